@@ -1,0 +1,153 @@
+#!/usr/bin/env python
+"""Generate ``tests/golden/*.npz`` by running the REAL reference (TRIQS/maxent 1.2.0, staged from
+/root/reference by ``stage_reference.py``).  TEST INFRASTRUCTURE; runs only in the build container.
+
+Each fixture holds the inputs (tau, G, err, omega, alpha mesh, options) and the reference's own
+outputs (alpha, chi2, S, Q, probability, H, A, n_iter, analyzer picks).  Input data that comes from
+the reference's test fixtures (``test/python/g_tau_semicircular.dat``, ``elementwise_g_tau.npz``)
+is stored as arrays.
+
+    python oracle/make_golden.py            # all cases (~1 min)
+"""
+import os
+import sys
+import time
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from stage_reference import import_reference, REF  # noqa: E402
+
+warnings.filterwarnings("ignore")
+GOLD = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def run_reference(tm_mod, tau, G, err, omega_pts, alpha_mesh, cost_function="normal", probability=None,
+                  reduce_singular_space=1e-14, extra_analyzers=False):
+    """TauMaxEnt run through the reference's public API (python/tau_maxent.py)."""
+    m = tm_mod
+    kw = dict(cost_function=cost_function, probability=probability,
+              reduce_singular_space=reduce_singular_space)
+    tm = m.TauMaxEnt(**kw)
+    tm.set_verbosity(m.VerbosityFlags.Quiet)
+    tm.set_G_tau_data(np.array(tau), np.array(G))
+    tm.omega = m.DataOmegaMesh(np.array(omega_pts))
+    tm.alpha_mesh = m.DataAlphaMesh(np.array(alpha_mesh))
+    tm.set_error(err)
+    t0 = time.time()
+    res = tm.run()
+    wall = time.time() - t0
+    out = dict(tau=np.array(tau), G=np.array(G), err=np.asarray(err, dtype=float), omega=np.array(omega_pts),
+               alpha_mesh=np.array(alpha_mesh), variant=cost_function,
+               use_probability=probability is not None, reduce_singular_space=reduce_singular_space,
+               ref_alpha=np.array(res.alpha), ref_chi2=np.array(res.chi2), ref_S=np.array(res.S),
+               ref_Q=np.array(res.Q), ref_probability=np.array(res.probability, dtype=float),
+               ref_H=np.array(res.H), ref_A=np.array(res.A), ref_v=np.array(res.v),
+               ref_n_sv=len(tm.K.S), ref_wall=wall,
+               ref_K_S=np.array(tm.K.S), ref_D=np.array(tm.D.D))
+    for name, ar in res.analyzer_results.items():
+        if isinstance(ar, dict) or hasattr(ar, "keys"):
+            if "alpha_index" in ar:
+                out["ref_idx_" + name] = int(ar["alpha_index"])
+            if "A_out" in ar and ar["A_out"] is not None:
+                out["ref_Aout_" + name] = np.array(ar["A_out"])
+    return out, tm, res
+
+
+def synthetic(n_tau, n_omega, seed=1234, mu=1.0, sigma=1e-4, beta=40.0):
+    """SURVEY.md 8(d) recipe, built with the reference's own mesh/kernel classes."""
+    m = import_reference()
+    tau = np.linspace(0, beta, n_tau)
+    omega = m.HyperbolicOmegaMesh(-10, 10, n_omega)
+    K = m.TauKernel(tau, omega, beta)
+    A = np.exp(-(omega - mu)**2 / (2 * 0.5**2))
+    A /= np.trapz(A, omega)
+    G_exact = np.dot(K.K_delta, A)
+    np.random.seed(seed)
+    G = G_exact + sigma * np.random.randn(n_tau)
+    return tau, np.array(G), np.array(omega)
+
+
+def main():
+    m = import_reference()
+    os.makedirs(GOLD, exist_ok=True)
+    tests = os.path.join(REF, "test", "python")
+
+    # --- G1: the reference's own known-answer test (test/python/tau_maxent.py:31-45,134-135) ----
+    dat = np.loadtxt(os.path.join(tests, "g_tau_semicircular.dat"))
+    np.random.seed(9)
+    tau, G0 = dat[:, 0], dat[:, 1]
+    G = G0 + 1.e-3 * np.random.randn(len(G0))
+    omega = m.HyperbolicOmegaMesh(omega_min=-10, omega_max=10, n_points=200)
+    amesh = m.LogAlphaMesh(alpha_min=0.08, n_points=5)
+    out, _, _ = run_reference(m, tau, G, 1.e-3, omega, amesh, probability="normal")
+    known = np.array([-8476.52812836, -2343.02752796, -704.28318351, -280.26627323, -175.30592555])
+    np.testing.assert_almost_equal(out["ref_probability"], known, 6)
+    out["known_probability"] = known
+    np.savez_compressed(os.path.join(GOLD, "g1_semicircular_prob.npz"), **out)
+    print("g1", out["ref_n_sv"], out["ref_wall"])
+
+    # --- G2: synthetic 200 x 100, 20 alphas, probability, truncated singular space --------------
+    tau, G, om = synthetic(200, 100)
+    amesh = m.LogAlphaMesh(0.01, 2000, 20)
+    out, _, _ = run_reference(m, tau, G, 1.e-4, om, amesh, probability="normal", reduce_singular_space=1e-11)
+    np.savez_compressed(os.path.join(GOLD, "g2_synth_200x100.npz"), **out)
+    print("g2", out["ref_n_sv"], out["ref_wall"], out.get("ref_idx_LineFitAnalyzer"))
+
+    # --- G3: plusminus, off-diagonal element of the elementwise fixture -------------------------
+    with np.load(os.path.join(tests, "elementwise_g_tau.npz")) as data:
+        tau_e = data["tau"]
+        G_e = data["G_tau_noise"]
+    om80 = m.HyperbolicOmegaMesh(omega_min=-10, omega_max=10, n_points=80)
+    am8 = m.LogAlphaMesh(alpha_min=0.05, alpha_max=500, n_points=8)
+    out, _, _ = run_reference(m, tau_e, G_e[0, 1], 1.e-3, om80, am8, cost_function="plusminus")
+    np.savez_compressed(os.path.join(GOLD, "g3_plusminus_offdiag.npz"), **out)
+    print("g3", out["ref_n_sv"], out["ref_wall"])
+
+    # --- G4: Bryan cost function on the G2 data ---------------------------------------------------
+    out, _, _ = run_reference(m, tau, G, 1.e-4, om, amesh, cost_function="bryan", reduce_singular_space=1e-11)
+    np.savez_compressed(os.path.join(GOLD, "g4_bryan_200x100.npz"), **out)
+    print("g4", out["ref_n_sv"], out["ref_wall"])
+
+    # --- G5: BASELINE config 1 (n_tau=1000, n_omega=400, 60 alphas), cut 1e-11 ---------------------
+    tau1, G1, om1 = synthetic(1000, 400)
+    am60 = m.LogAlphaMesh(0.01, 2000, 60)
+    out, _, _ = run_reference(m, tau1, G1, 1.e-4, om1, am60, reduce_singular_space=1e-11)
+    for k in ("ref_H", "ref_v"):
+        out.pop(k)                      # A is enough; keeps the fixture small
+    np.savez_compressed(os.path.join(GOLD, "g5_config1_cut1e-11.npz"), **out)
+    print("g5", out["ref_n_sv"], out["ref_wall"], out.get("ref_idx_LineFitAnalyzer"),
+          out.get("ref_idx_Chi2CurvatureAnalyzer"), out.get("ref_idx_EntropyAnalyzer"))
+
+    # --- G5b: same with the reference's default cut 1e-14 (n_sv = 76) -----------------------------
+    out, _, _ = run_reference(m, tau1, G1, 1.e-4, om1, am60, reduce_singular_space=1e-14)
+    for k in ("ref_H", "ref_v"):
+        out.pop(k)
+    np.savez_compressed(os.path.join(GOLD, "g5b_config1_default_cut.npz"), **out)
+    print("g5b", out["ref_n_sv"], out["ref_wall"], out.get("ref_idx_LineFitAnalyzer"))
+
+    # --- G6: BASELINE config 2 = ElementwiseMaxEnt on the 2x2 fixture ----------------------------
+    #     (test/python/elementwise_maxent.py:110-117, use_hermiticity=True)
+    ew = m.ElementwiseMaxEnt(use_hermiticity=True)
+    ew.set_verbosity(m.VerbosityFlags.Quiet)
+    ew.set_G_tau_data(tau_e, G_e)
+    ew.omega = m.HyperbolicOmegaMesh(omega_min=-10, omega_max=10, n_points=80)
+    ew.alpha_mesh = m.LogAlphaMesh(alpha_min=0.05, alpha_max=500, n_points=8)
+    ew.set_error(1.e-3)
+    res = ew.run()
+    out = dict(tau=tau_e, G=G_e, err=1.e-3, omega=np.array(ew.omega), alpha_mesh=np.array(ew.alpha_mesh),
+               ref_alpha=np.array(res.alpha), ref_chi2=np.array(res.chi2), ref_S=np.array(res.S),
+               ref_A=np.array(res.A), ref_A_out=np.array(res.A_out))
+    for i in range(2):
+        for j in range(2):
+            ar = res.analyzer_results[i][j]
+            if ar:
+                out["ref_idx_LineFitAnalyzer_%d%d" % (i, j)] = int(ar["LineFitAnalyzer"]["alpha_index"])
+    np.savez_compressed(os.path.join(GOLD, "g6_elementwise_2x2.npz"), **out)
+    print("g6 done")
+
+
+if __name__ == "__main__":
+    main()
