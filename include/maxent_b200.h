@@ -1,0 +1,145 @@
+/*
+ * maxent_b200 -- C ABI of the B200-native MaxEnt alpha-sweep engine.
+ *
+ * The reference (TRIQS/maxent 1.2.0) is pure Python and has no FFI; the seam this library plugs
+ * into is MaxEntLoop.run (python/maxent_loop.py:144-302) and the functions below it (SURVEY.md
+ * section 8(a) R1-R13).  Each entry point names the reference code it replaces.
+ *
+ * Conventions: plain pointers and sizes, no torch / C++ types.  All pointers are DEVICE pointers
+ * unless the name ends in _host.  Row-major contiguous float64 unless stated.  Every call is
+ * asynchronous on `stream` (a cudaStream_t passed as void*), keeps no global state, and returns 0
+ * or a negative MX_ERR_* code; nothing throws across the ABI.
+ */
+#ifndef MAXENT_B200_H
+#define MAXENT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MX_OK                0
+#define MX_ERR_BAD_ARG      -1
+#define MX_ERR_UNSUPPORTED  -2   /* e.g. n_sv > MX_MAX_NSV */
+#define MX_ERR_CUDA         -3
+#define MX_ERR_NO_DEVICE    -4
+
+#define MX_MAX_NSV         128   /* singular-space dimension the fused path supports */
+
+/* cost-function variants (python/maxent_loop.py:106-121) */
+#define MX_VARIANT_NORMAL    0   /* MaxEntCostFunction + NormalEntropy + NormalH_of_v   */
+#define MX_VARIANT_PLUSMINUS 1   /* MaxEntCostFunction + PlusMinusEntropy + PlusMinusH_of_v */
+#define MX_VARIANT_BRYAN     2   /* BryanCostFunction */
+
+/* analyzer slots in mx_analyze outputs */
+#define MX_AN_LINEFIT        0   /* python/analyzers/linefit_analyzer.py        */
+#define MX_AN_CHI2CURV       1   /* python/analyzers/chi2_curvature_analyzer.py */
+#define MX_AN_ENTROPY        2   /* python/analyzers/entropy_analyzer.py        */
+#define MX_AN_CLASSIC        3   /* python/analyzers/classic_analyzer.py        */
+#define MX_AN_BRYAN          4   /* python/analyzers/bryan_analyzer.py          */
+#define MX_N_ANALYZERS       5
+
+/* per-(spectrum, alpha) status bits */
+#define MX_STATUS_CONVERGED  1   /* LevenbergMinimizer.converged (levenberg_minimizer.py:162-174) */
+#define MX_STATUS_SKIPPED    2   /* max|G| < G_threshold (maxent_loop.py:174-179) */
+
+/* Levenberg-Marquardt parameters = LevenbergMinimizer.__init__ (levenberg_minimizer.py:92-121)
+ * with the default convergence MaxDerivative(1e-4) | RelativeFunctionChange(1e-16). */
+typedef struct {
+    int32_t maxiter;          /* 1000  */
+    int32_t miniter;          /* 0     */
+    double  mu0;              /* 1e-18 */
+    double  nu;               /* 1.3   */
+    double  max_mu;           /* 1e20  */
+    double  conv_max_derivative;   /* 1e-4  */
+    double  conv_rel_change;       /* 1e-16 */
+} MxLMParams;
+
+/* Problem state shared by every spectrum of a batch (built once per kernel/err by
+ * mx_layout_V + the host-side preparation; see DESIGN.md "data layout"). */
+typedef struct {
+    int32_t n_tau;            /* rows of the (possibly covariance-rotated) data space       */
+    int32_t n_omega;
+    int32_t n_sv;             /* singular-space dimension s  (<= MX_MAX_NSV)                 */
+    int32_t n_alpha;
+    int32_t variant;          /* MX_VARIANT_*                                                */
+    int32_t want_probability; /* NormalLogProbability (probabilities.py:76-85)               */
+    double  chi2_factor;      /* MaxEntCostFunction chi2_factor (cost_function.py:43-53)     */
+    const double* Vt;         /* swizzled tile-major V' written by mx_layout_V               */
+    const double* Qw;         /* [n_tau, n_sv]  sqrt(W) Q : g~ = Qw^T G                      */
+    const double* Qo;         /* [n_tau, n_sv]  Q (orthonormal) for the out-of-range residual */
+    const double* sqrtw;      /* [n_tau]        1/err                                         */
+    const double* xi;         /* [n_sv]         singular values of sqrt(W) K V_s             */
+    const double* D;          /* [n_omega]      default model incl. delta omega              */
+    const double* delta;      /* [n_omega]      trapezoid weights of the omega mesh          */
+    const double* alpha;      /* [n_alpha]      alpha * scale_alpha, descending              */
+    const double* v0;         /* [n_sv]         initial v' (maxent_loop.py:196-203)          */
+    MxLMParams lm;
+} MxProblem;
+
+/* Outputs of the alpha sweep; any pointer may be NULL to skip that output (chi2/S/Q required). */
+typedef struct {
+    double*  v;        /* [B, n_alpha, n_sv]     solution in the (rotated) singular basis  */
+    double*  A;        /* [B, n_alpha, n_omega]  A_alpha(omega) = H / delta (functions.py:947-952) */
+    double*  chi2;     /* [B, n_alpha]   */
+    double*  S;        /* [B, n_alpha]   */
+    double*  Q;        /* [B, n_alpha]   */
+    double*  logp;     /* [B, n_alpha]   NaN if !want_probability */
+    int32_t* n_iter;   /* [B, n_alpha]   LevenbergMinimizer.n_iter_last */
+    int32_t* n_qeval;  /* [B, n_alpha]   cost-function evaluations (rounds) */
+    int32_t* n_solve;  /* [B, n_alpha]   dense solves attempted */
+    int32_t* status;   /* [B, n_alpha]   MX_STATUS_* bits */
+} MxSweepOut;
+
+/* Library / device info.  Returns the number of SMs of the current device (or <0). */
+int mx_device_sm_count(void);
+const char* mx_version(void);
+
+/* Size in doubles of the swizzled V buffer for (n_omega, n_sv). */
+int64_t mx_layout_V_size(int32_t n_omega, int32_t n_sv);
+
+/* Re-tile V [n_omega, n_sv] (row-major) into the bank-conflict-free 8x8 tile layout the sweep
+ * kernel streams.  Replaces nothing in the reference (layout only). */
+int mx_layout_V(const double* V, int32_t n_omega, int32_t n_sv, double* Vt, void* stream);
+
+/* TauKernel._fill_values (python/kernels.py:244-266): K[n_tau, n_omega] on the device. */
+int mx_tau_kernel(const double* tau, const double* omega, int32_t n_tau, int32_t n_omega,
+                  double beta, double* K, void* stream);
+
+/* One-sided Jacobi SVD of K[m, n] (m >= n), replaces np.linalg.svd in KernelSVD.svd
+ * (python/kernels.py:53-64).  U[m, n], S[n] (descending), V[n, n]; work = m*n doubles. */
+int mx_svd_jacobi(const double* K, int32_t m, int32_t n, double* U, double* S, double* V,
+                  double* work, int32_t max_sweeps, int32_t* sweeps_done, void* stream);
+
+/* Project the data of B spectra into the singular space:
+ *   gt[b] = Qw^T G[b]  and  c0[b] = | sqrtw*G[b] - Qo gt[b] |^2
+ * so that chi2(H) = sum_i (xi_i y_i - gt_i)^2 + c0 with y = V'^T H   (NormalChi2.f, functions.py:358-360). */
+int mx_project_data(const MxProblem* p, const double* G /*[B, n_tau]*/, int32_t B,
+                    double* gt /*[B, n_sv]*/, double* c0 /*[B]*/, void* stream);
+
+/* The fused alpha sweep = the `for alpha in alpha_mesh` loop of MaxEntLoop.run
+ * (python/maxent_loop.py:241-266) with LevenbergMinimizer.minimize
+ * (python/minimizers/levenberg_minimizer.py:123-248), the cost functions
+ * (python/cost_functions/maxent_cost_function.py:68-165, bryan_cost_function.py:57-128) and
+ * NormalLogProbability.f (python/probabilities.py:76-85) for B independent spectra.
+ * `work_counter` is one int32 on the device (zeroed by the call).  */
+int mx_alpha_sweep(const MxProblem* p, const double* gt, const double* c0, int32_t B,
+                   const MxSweepOut* out, int32_t* work_counter, void* stream);
+
+/* Dynamic shared memory the sweep kernel will request and spectra per CTA it will use for n_sv
+ * (introspection for tests / DESIGN.md). */
+int mx_sweep_config(int32_t n_sv, int32_t* spectra_per_cta, int32_t* smem_bytes, int32_t* threads);
+
+/* Analyzer reductions (python/analyzers/*.py) for B spectra:
+ * alpha_index[B, MX_N_ANALYZERS] (-1 = not available), A_out[B, MX_N_ANALYZERS, n_omega]. */
+int mx_analyze(const double* alpha /*[n_alpha]*/, const double* chi2, const double* S,
+               const double* logp /* may be NULL */, const double* A /*[B, n_alpha, n_omega]*/,
+               int32_t B, int32_t n_alpha, int32_t n_omega, double gamma, int32_t linefit_deg,
+               int32_t bryan_by_integration,
+               int32_t* alpha_index, double* A_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAXENT_B200_H */

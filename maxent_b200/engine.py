@@ -1,0 +1,199 @@
+"""Host driver of the fused alpha sweep: prepares the state shared by a batch of spectra
+(kernel SVD, truncation, whitening rotation, V' re-tiling, initial v) and calls the C ABI.
+
+PyTorch is used for device memory, streams and the one-time small dense factorisations only; the
+hot path (projection, alpha sweep, analyzers) runs in libmaxent_b200.so.  Nothing here runs the
+algorithm on the CPU: a missing library or a missing CUDA device is an error.
+
+Reference seam: MaxEntLoop.run (python/maxent_loop.py:144-302).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+_F64 = None
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _ptr(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+class LMParams(object):
+    """LevenbergMinimizer parameters (python/minimizers/levenberg_minimizer.py:92-121)."""
+
+    def __init__(self, maxiter=1000, miniter=0, mu0=1.e-18, nu=1.3, max_mu=1.e20,
+                 conv_max_derivative=1.e-4, conv_rel_change=1.e-16):
+        if nu <= 1.0:
+            raise Exception('If nu <= 1, there will be an infinite loop.')   # levenberg_minimizer.py:139-140
+        self.maxiter, self.miniter, self.mu0, self.nu, self.max_mu = maxiter, miniter, mu0, nu, max_mu
+        self.conv_max_derivative, self.conv_rel_change = conv_max_derivative, conv_rel_change
+
+    def c_struct(self):
+        return _lib.MxLMParams(int(self.maxiter), int(self.miniter), float(self.mu0), float(self.nu),
+                               float(self.max_mu), float(self.conv_max_derivative), float(self.conv_rel_change))
+
+
+class SharedProblem(object):
+    """Everything a batch of spectra shares: K = U S V^T truncated at `reduce_singular_space`
+    (python/kernels.py:101-122), rotated so that chi2 is diagonal in the singular space:
+
+        M = diag(1/err) K V_s = Q Xi P^T ,  V' = V_s P ,  chi2(H) = |Xi V'^T H - Q^T G/err|^2 + c0
+
+    (for a scalar err: Q = U_s, Xi = S_s/err, P = 1).  The Levenberg iterates are invariant under
+    this rotation because mu*1 is."""
+
+    def __init__(self, K, err, D, delta, variant="normal", reduce_singular_space=1.e-14, device=None,
+                 svd="jacobi", A_init=None, max_nsv=None):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise _lib.MaxEntLibraryError("maxent_b200 needs a CUDA device (no CPU fallback)")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda" if device is None else device)
+        f64 = torch.float64
+        dev = self.device
+        with torch.cuda.device(dev):
+            K = torch.as_tensor(np.ascontiguousarray(K, dtype=np.float64) if not torch.is_tensor(K) else K,
+                                dtype=f64, device=dev).contiguous()
+            n_tau, n_omega = K.shape
+            self.n_tau, self.n_omega = int(n_tau), int(n_omega)
+            self.variant = variant
+            # ---- SVD of the kernel (KernelSVD.svd, python/kernels.py:53-64) ----
+            U, S, V = self._svd(K, svd)
+            thr = reduce_singular_space
+            keep = torch.nonzero(S >= (thr if thr is not None else -1.0)).flatten()
+            cap = _lib.MX_MAX_NSV if max_nsv is None else max_nsv
+            self.n_sv_uncapped = int(keep.numel())
+            if keep.numel() > cap:
+                keep = keep[:cap]
+            U, S, V = U[:, keep].contiguous(), S[keep].contiguous(), V[:, keep].contiguous()
+            self.U, self.S, self.V = U, S, V
+            s = int(S.numel())
+            self.n_sv = s
+            # ---- whitening rotation ----
+            err_np = np.asarray(err, dtype=np.float64) * np.ones(self.n_tau)
+            err_t = torch.as_tensor(err_np, dtype=f64, device=dev)
+            sqrtw = 1.0 / err_t
+            if np.all(err_np == err_np[0]):
+                Q, Xi, P = U, S / err_np[0], None
+            else:
+                M = sqrtw[:, None] * (K @ V)
+                Q, Xi, Pt = torch.linalg.svd(M, full_matrices=False)
+                P = Pt.transpose(0, 1).contiguous()
+            self.P = P
+            self.Vp = V if P is None else (V @ P).contiguous()
+            self.Q = Q.contiguous()
+            self.Qw = (sqrtw[:, None] * Q).contiguous()
+            self.sqrtw = sqrtw.contiguous()
+            self.xi = Xi.contiguous()
+            self.D = torch.as_tensor(np.asarray(D, dtype=np.float64), dtype=f64, device=dev).contiguous()
+            self.delta = torch.as_tensor(np.asarray(delta, dtype=np.float64), dtype=f64, device=dev).contiguous()
+            # ---- initial v (python/maxent_loop.py:196-203; quirk: D*delta although D holds delta) ----
+            H0 = (self.D if A_init is None else torch.as_tensor(np.asarray(A_init, dtype=np.float64), device=dev)) * self.delta
+            if variant == "plusminus":
+                arg = (H0 + torch.sqrt(H0**2 + 4 * self.D**2)) / (2 * self.D)   # functions.py:793-796
+            else:
+                arg = H0 / self.D                                               # functions.py:753-755
+            arg = torch.where(arg.abs() <= 1e-100, torch.full_like(arg, 1e-100), arg)
+            self.v0 = (self.Vp.transpose(0, 1) @ torch.log(arg)).contiguous()
+            # ---- re-tile V' for the sweep kernel ----
+            n = int(self.lib.mx_layout_V_size(self.n_omega, s))
+            if n < 0:
+                raise _lib.MaxEntLibraryError("n_sv=%d outside the fused path (max %d)" % (s, _lib.MX_MAX_NSV))
+            self.Vt = torch.empty(n, dtype=f64, device=dev)
+            stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(self.lib.mx_layout_V(_ptr(self.Vp), self.n_omega, s, _ptr(self.Vt), stream), "mx_layout_V")
+            self.config = _lib.sweep_config(s)
+
+    def _svd(self, K, method):
+        torch = _torch()
+        if method == "jacobi":
+            m, n = K.shape
+            tr = m < n
+            Kk = K.transpose(0, 1).contiguous() if tr else K
+            m2, n2 = Kk.shape
+            U = torch.empty((m2, n2), dtype=torch.float64, device=K.device)
+            S = torch.empty((n2,), dtype=torch.float64, device=K.device)
+            V = torch.empty((n2, n2), dtype=torch.float64, device=K.device)
+            work = torch.empty((m2 * n2 + n2 * n2 + n2 + 8,), dtype=torch.float64, device=K.device)
+            sweeps = ctypes.c_int32(0)
+            stream = ctypes.c_void_p(torch.cuda.current_stream(K.device).cuda_stream)
+            _lib.check(self.lib.mx_svd_jacobi(_ptr(Kk), m2, n2, _ptr(U), _ptr(S), _ptr(V), _ptr(work), 60,
+                                              ctypes.byref(sweeps), stream), "mx_svd_jacobi")
+            self.svd_sweeps = sweeps.value
+            return (V, S, U) if tr else (U, S, V)
+        elif method == "torch":
+            U, S, Vh = torch.linalg.svd(K, full_matrices=False)
+            return U.contiguous(), S.contiguous(), Vh.transpose(0, 1).contiguous()
+        raise ValueError("svd must be 'jacobi' or 'torch'")
+
+    def v_to_reference_basis(self, v):
+        """v' (rotated basis) -> v in the basis of the truncated SVD of K."""
+        return v if self.P is None else v @ self.P.transpose(0, 1)
+
+
+class SweepResult(object):
+    """Device tensors produced by one call of the fused sweep (+ analyzers)."""
+    __slots__ = ("alpha", "v", "A", "chi2", "S", "Q", "logp", "n_iter", "n_qeval", "n_solve", "status",
+                 "alpha_index", "A_out", "n_sv")
+
+
+def run_sweep(prob, G, alpha_eff, probability=False, lm=None, chi2_factor=1.0, want_A=True, want_v=True,
+              analyze=True, gamma=0.2, linefit_deg=0, bryan_by_integration=False):
+    """Fused alpha sweep for a batch G[B, n_tau] sharing `prob`.  `alpha_eff` = alpha * scale_alpha, descending.
+    Everything stays on the device; returns a SweepResult of torch tensors."""
+    torch = _torch()
+    lib = prob.lib
+    dev = prob.device
+    f64, i32 = torch.float64, torch.int32
+    lm = LMParams() if lm is None else lm
+    with torch.cuda.device(dev):
+        G = torch.as_tensor(G, dtype=f64, device=dev)
+        if G.dim() == 1:
+            G = G[None, :]
+        G = G.contiguous()
+        B = int(G.shape[0])
+        if G.shape[1] != prob.n_tau:
+            raise ValueError("G has %d data points, kernel has %d" % (G.shape[1], prob.n_tau))
+        alpha = torch.as_tensor(np.asarray(alpha_eff, dtype=np.float64), dtype=f64, device=dev).contiguous()
+        n_alpha, s, n_omega = int(alpha.numel()), prob.n_sv, prob.n_omega
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        p = _lib.MxProblem(prob.n_tau, n_omega, s, n_alpha, _lib.VARIANTS[prob.variant], int(bool(probability)),
+                           float(chi2_factor), _ptr(prob.Vt), _ptr(prob.Qw), _ptr(prob.Q), _ptr(prob.sqrtw),
+                           _ptr(prob.xi), _ptr(prob.D), _ptr(prob.delta), _ptr(alpha), _ptr(prob.v0), lm.c_struct())
+        gt = torch.empty((B, s), dtype=f64, device=dev)
+        c0 = torch.empty((B,), dtype=f64, device=dev)
+        _lib.check(lib.mx_project_data(ctypes.byref(p), _ptr(G), B, _ptr(gt), _ptr(c0), stream), "mx_project_data")
+        r = SweepResult()
+        r.alpha = alpha
+        r.n_sv = s
+        r.v = torch.empty((B, n_alpha, s), dtype=f64, device=dev) if want_v else None
+        r.A = torch.empty((B, n_alpha, n_omega), dtype=f64, device=dev) if want_A else None
+        r.chi2 = torch.empty((B, n_alpha), dtype=f64, device=dev)
+        r.S = torch.empty((B, n_alpha), dtype=f64, device=dev)
+        r.Q = torch.empty((B, n_alpha), dtype=f64, device=dev)
+        r.logp = torch.full((B, n_alpha), float("nan"), dtype=f64, device=dev)
+        r.n_iter = torch.zeros((B, n_alpha), dtype=i32, device=dev)
+        r.n_qeval = torch.zeros((B, n_alpha), dtype=i32, device=dev)
+        r.n_solve = torch.zeros((B, n_alpha), dtype=i32, device=dev)
+        r.status = torch.zeros((B, n_alpha), dtype=i32, device=dev)
+        counter = torch.zeros((1,), dtype=i32, device=dev)
+        out = _lib.MxSweepOut(_ptr(r.v), _ptr(r.A), _ptr(r.chi2), _ptr(r.S), _ptr(r.Q), _ptr(r.logp),
+                              _ptr(r.n_iter), _ptr(r.n_qeval), _ptr(r.n_solve), _ptr(r.status))
+        _lib.check(lib.mx_alpha_sweep(ctypes.byref(p), _ptr(gt), _ptr(c0), B, ctypes.byref(out), _ptr(counter), stream),
+                   "mx_alpha_sweep")
+        r.alpha_index = r.A_out = None
+        if analyze:
+            r.alpha_index = torch.full((B, _lib.N_ANALYZERS), -1, dtype=i32, device=dev)
+            r.A_out = torch.empty((B, _lib.N_ANALYZERS, n_omega), dtype=f64, device=dev) if want_A else None
+            _lib.check(lib.mx_analyze(_ptr(alpha), _ptr(r.chi2), _ptr(r.S), _ptr(r.logp) if probability else None,
+                                      _ptr(r.A), B, n_alpha, n_omega, float(gamma), int(linefit_deg),
+                                      int(bool(bryan_by_integration)), _ptr(r.alpha_index), _ptr(r.A_out), stream),
+                       "mx_analyze")
+        return r
