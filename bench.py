@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""Headline benchmark: spectra/sec for the full 60-alpha MaxEnt loop in FP64 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+
+A "step" is one pass of the hot path (data projection -> fused alpha sweep -> analyzers) over one
+synthetic bootstrap batch: per GPU, `--spectra` (default 8192 = BASELINE config 5's per-GPU shard of the
+65,536-spectrum batch) spectra with n_tau=2000, n_omega=1000, 60 alphas, reduce_singular_space=1e-11
+(SURVEY.md 8(d) C5 recipe).  Weak scaling: every rank owns its own shard, no data-path collective;
+one NCCL gather of the result arrays closes the e2e step.
+
+One JSON line is printed by rank 0 (see the contract in the task statement).  `value` = device-resident
+throughput, `e2e` = through the public batched API with pinned-host inputs/outputs, `roofline` = the
+sweep kernel's achieved algorithmic FP64 FLOP/s against the measured FP64 peak, `cpu_baseline` = the
+oracle port of the reference timed on the host cores in the same run (rank 0, N=1).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "spectra/sec (full 60-alpha MaxEnt loop, FP64)"
+UNIT = "spectra/s"
+# Measured FP64 peak of this pool's B200 (tools/fp64_microbench.cu -> profiles/r01_fp64_microbench.json,
+# DMMA m8n8k4 and DFMA both saturate at 37.0 TFLOP/s).  MEASURED_PEAKS.json holds no FP64 figure.
+FP64_PEAK_FALLBACK_TFLOPS = 37.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--spectra", type=int, default=8192, help="spectra per GPU and step")
+    ap.add_argument("--n-tau", type=int, default=2000)
+    ap.add_argument("--n-omega", type=int, default=1000)
+    ap.add_argument("--n-alpha", type=int, default=60)
+    ap.add_argument("--thr", type=float, default=1e-11, help="reduce_singular_space")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-procs", type=int, default=0)
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return "bootstrap batch C5 shard: %d spectra/GPU, n_tau=%d, n_omega=%d, %d alphas, cut %g" % (
+        a.spectra, a.n_tau, a.n_omega, a.n_alpha, a.thr)
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline
+# --------------------------------------------------------------------------------------------------
+def cpu_baseline(a, spectra=None, procs=None):
+    procs = procs or a.cpu_procs or (os.cpu_count() or 1)
+    spectra = spectra or procs
+    cmd = [sys.executable, "-m", "oracle.cpu_baseline", "--n-tau", str(a.n_tau), "--n-omega", str(a.n_omega),
+           "--n-alpha", str(a.n_alpha), "--spectra", str(spectra), "--procs", str(procs), "--thr", str(a.thr)]
+    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("cpu baseline failed: " + out.stderr[-2000:])
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def cpu_baseline_block(r):
+    return {"value": r["spectra_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+            "sample": "first %d spectra of the batch, full alpha loop, one process per spectrum x %d BLAS thread "
+                      "(oracle/maxent_oracle.py = numpy port pinned bit-identically to TauMaxEnt.run; K^T W K setup "
+                      "through BLAS); wall %.1f s; per-spectrum %.1f-%.1f s; LM iterations %d-%d; n_sv=%d"
+                      % (r["spectra"], r["blas_threads"], r["wall_s"], min(r["per_spectrum_s"]),
+                         max(r["per_spectrum_s"]), min(r["n_iter"]), max(r["n_iter"]), r["n_sv"])}
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    budget = float(os.environ.get("MAXENT_REF_BUDGET_S", "420"))
+    t_begin = time.time()
+    small = argparse.Namespace(**vars(a))
+    small.n_tau, small.n_omega = 200, 100
+    for _ in range(a.warmup):            # warm-up: process pool + BLAS on a small kernel (a full-size step is ~1 min)
+        cpu_baseline(small)
+    rows = []
+    for k in range(a.steps):
+        rows.append(cpu_baseline(a))
+        if time.time() - t_begin > budget and k + 1 < a.steps:
+            break
+    n = sum(r["spectra"] for r in rows)
+    wall = sum(r["wall_s"] for r in rows)
+    val = n / wall
+    merged = dict(rows[-1])
+    merged.update(spectra_per_s=val)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus,
+            "steps": len(rows), "steps_requested": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1000.0 * wall / len(rows), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "note": "CPU arm: each step = one bounded sample (cores spectra); "
+                       "warm-up steps use a 200x100 kernel; stops early after MAXENT_REF_BUDGET_S=%g s" % budget},
+            "cpu_baseline": cpu_baseline_block(merged),
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# native arm
+# --------------------------------------------------------------------------------------------------
+def algorithmic_flops(n_iter, n_q, n_s, n_alpha_total, n_omega, s, probability):
+    """FP64 FLOPs of the singular-space algorithm the kernel implements ('roofline'):
+       per cost-function evaluation F_Q = 4 n_omega s + 8 n_omega   (x = V v, y = V^T H, pointwise exp/entropy)
+       per LM iteration             F_H = n_omega s^2 + 2 s^3 + 4 s^2  (symmetric half of Z, J = Z Lambda Z + alpha Z, f = Z u)
+       per solve                    F_S = s^3 / 3 + 2 s^2
+    The survey's figure (section 8(d)) adds 2 n_tau s per evaluation for r = U Sigma y - G, which this
+    formulation does not need (chi2 is diagonal in the rotated basis); it is reported as flops_survey."""
+    FQ = 4.0 * n_omega * s + 8.0 * n_omega
+    FH = n_omega * s * s + 2.0 * s ** 3 + 4.0 * s * s
+    FS = s ** 3 / 3.0 + 2.0 * s * s
+    F = n_iter * FH + n_q * FQ + n_s * FS
+    if probability:
+        F += n_alpha_total * (n_omega * s * s + s ** 3 / 3.0)
+    return F
+
+
+def run_native(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from maxent_b200 import engine, batched
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl native needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- the job: one BatchedTauMaxEnt per rank over its shard of the bootstrap batch ------------
+    B = a.spectra
+    job = batched.BatchedTauMaxEnt(reduce_singular_space=a.thr, device=dev)
+    t0 = time.time()
+    G_host = batched.synthetic_bootstrap_batch(a.n_tau, a.n_omega, B, first=rank * B, seed=5, pin=True)
+    job.set_kernel_tau(np.linspace(0.0, 40.0, a.n_tau), batched.hyperbolic_omega(-10.0, 10.0, a.n_omega), beta=40.0)
+    job.set_alpha_mesh_log(0.01, 2000.0, a.n_alpha)
+    job.set_error(1.e-4)
+    job.prepare()                                   # kernel fill, Jacobi SVD, truncation, V' layout (once per kernel)
+    torch.cuda.synchronize()
+    setup_s = time.time() - t0
+    prob = job.problem
+
+    G_dev = G_host.to(dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident steps ---------------------------------------------------------------------
+    for _ in range(a.warmup):
+        res = job.run_device(G_dev)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sweep_ms = 0.0
+    ev0.record()
+    for _ in range(a.steps):
+        res = job.run_device(G_dev)
+        sweep_ms += 0.0
+    ev1.record()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+
+    # ---- the dominant kernel alone (CUDA events around mx_alpha_sweep on the launching stream) ------
+    k_ms = []
+    for _ in range(max(1, min(a.steps, 3))):
+        k_ms.append(job.time_sweep_kernel(G_dev))
+    kernel_ms = sum(k_ms) / len(k_ms)
+    n_iter = int(res.n_iter.sum()); n_q = int(res.n_qeval.sum()); n_s = int(res.n_solve.sum())
+    s = prob.n_sv
+    flops = algorithmic_flops(n_iter, n_q, n_s, B * a.n_alpha, a.n_omega, s, False)
+    flops_survey = flops + n_q * 2.0 * a.n_tau * s
+    peak = FP64_PEAK_FALLBACK_TFLOPS
+    peak_src = "measured FP64 DMMA/DFMA peak of this pool's B200, profiles/r01_fp64_microbench.json (MEASURED_PEAKS.json has no FP64 entry)"
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        for key in ("fp64_tflops", "dmma_tflops"):
+            if key in mp:
+                peak, peak_src = float(mp[key]), "MEASURED_PEAKS.json:" + key
+    except Exception:
+        pass
+    achieved = flops / (kernel_ms * 1e-3) / 1e12
+
+    # ---- end to end through the public API: pinned host G in, pinned host results out ---------------
+    for _ in range(max(1, min(a.warmup, 2))):
+        out = job.run(G_host)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        out = job.run(G_host)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    h2d, d2h = out.h2d_bytes, out.d2h_bytes
+
+    # ---- max over ranks -------------------------------------------------------------------------------
+    t = torch.tensor([dev_ms, e2e_ms, kernel_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # the one collective of the job: gather the analyzer outputs on rank 0 (NCCL over NVLink)
+        gathered = batched.gather_results(out, dst=0)
+        if rank == 0:
+            assert gathered["alpha_index"].shape[0] == world * B
+    dev_ms, e2e_ms, kernel_ms_max = [float(x) for x in t.tolist()]
+
+    if rank == 0:
+        total = world * B * a.steps
+        value = total / (dev_ms * 1e-3)
+        e2e = total / (e2e_ms * 1e-3)
+        idx = res.alpha_index.cpu().numpy()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "n_sv": s, "parallelism": "spectra sharded x%d, no data-path collective" % world,
+                       "l2": "inputs/outputs larger than L2 (G %.0f MB, A(alpha) %.1f GB per step); V' (%.0f KB) is L2-resident by design"
+                             % (B * a.n_tau * 8 / 1e6, B * a.n_alpha * a.n_omega * 8 / 1e9, prob.Vt.numel() * 8 / 1e3),
+                       "setup_s_once_per_kernel": round(setup_s, 3), "svd_sweeps": getattr(prob, "svd_sweeps", None),
+                       "spectra_per_cta": prob.config["spectra_per_cta"], "smem_bytes": prob.config["smem_bytes"],
+                       "lm_iterations_per_spectrum": n_iter / B, "q_evals_per_spectrum": n_q / B, "solves_per_spectrum": n_s / B,
+                       "converged_frac": float((res.status & 1).double().mean()),
+                       "linefit_idx_hist": {int(k): int(v) for k, v in zip(*np.unique(idx[:, 0], return_counts=True))},
+                       "chi2curv_idx_hist": {int(k): int(v) for k, v in zip(*np.unique(idx[:, 1], return_counts=True))}},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / a.steps},
+            "gpu_launches": a.steps * job.launches_per_step,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "mx::sweep_kernel", "kernel_ms": kernel_ms,
+                         "kernel_share_of_step": kernel_ms / (dev_ms / a.steps),
+                         "flops_per_launch": flops, "flops_per_spectrum": flops / B,
+                         "flops_survey_formula_per_spectrum": flops_survey / B,
+                         "pipe": "FP64 (DMMA m8n8k4 + DFMA share one pipe on B200)", "peak_source": peak_src},
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline_block(cpu_baseline(a))
+            except Exception as e:        # the GPU numbers stay valid; say why the CPU leg is missing
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %s" % e}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_native(a)
+
+
+if __name__ == "__main__":
+    main()

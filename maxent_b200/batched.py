@@ -1,0 +1,290 @@
+"""Batched front end: many independent spectra that share one kernel (k-points, orbital elements,
+bootstrap samples) continued in ONE fused launch per GPU.
+
+The reference has no counterpart: "many spectra" is a Python ``for`` loop over ``TauMaxEnt.run``
+(doc/guide/blockgf.rst:10-18, python/elementwise_maxent.py:236-268).  This class sits beside the
+drop-in single-spectrum API and uses the same vocabulary (``set_G_tau_data``, ``set_error``, ``omega``,
+``alpha_mesh``, ``D``, ``reduce_singular_space``, ``scale_alpha``, ``G_threshold``).
+
+Multi-GPU: one process per GPU, each owning a contiguous shard of the batch (``shard_bounds``); the only
+collective is the final gather of the result arrays (``gather_results``).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib, engine
+from .alpha_meshes import LogAlphaMesh
+from .default_models import FlatDefaultModel
+from .omega_meshes import HyperbolicOmegaMesh, DataOmegaMesh
+
+ANALYZER_NAMES = ("LineFitAnalyzer", "Chi2CurvatureAnalyzer", "EntropyAnalyzer", "ClassicAnalyzer", "BryanAnalyzer")
+
+
+def hyperbolic_omega(omega_min, omega_max, n_points):
+    return HyperbolicOmegaMesh(omega_min, omega_max, n_points)
+
+
+def shard_bounds(n_total, world_size, rank):
+    """Contiguous, balanced split of ``n_total`` spectra over ``world_size`` ranks: [lo, hi) of ``rank``."""
+    base, rem = divmod(int(n_total), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def synthetic_bootstrap_batch(n_tau, n_omega, n_spectra, first=0, seed=5, beta=40.0, mu=1.0, width=0.5,
+                              sigma=1.e-4, pin=False):
+    """Synthetic G(tau) batch of the benchmark: a Gaussian A(omega) pushed through
+    the TauKernel plus sigma * N(0,1) noise, rows [first, first + n_spectra) of the seeded noise matrix.
+    Returns a (pinned) host float64 tensor [n_spectra, n_tau]."""
+    import torch
+    tau = np.linspace(0, beta, n_tau)
+    omega = HyperbolicOmegaMesh(-10, 10, n_omega)
+    w = np.asarray(omega)
+    A = np.exp(-(w - mu) ** 2 / (2 * width ** 2))
+    A /= np.sum(0.5 * (A[1:] + A[:-1]) * np.diff(w))
+    ww, tt = np.meshgrid(w, tau)
+    with np.errstate(over="ignore"):
+        K = np.where(ww >= 0, -np.exp(-ww * tt) / (np.exp(-beta * ww) + 1.0),
+                     -np.exp(np.minimum(ww, 0) * (beta - tt)) / (1.0 + np.exp(beta * np.minimum(ww, 0))))
+    G_exact = (K * omega.delta[None, :]) @ A
+    rng = np.random.default_rng(seed)
+    if first:
+        # rows [0, first) belong to lower ranks: skip them in blocks instead of materialising them
+        left = first
+        while left > 0:
+            blk = min(left, 4096)
+            rng.standard_normal((blk, n_tau))
+            left -= blk
+    G = G_exact[None, :] + sigma * rng.standard_normal((n_spectra, n_tau))
+    t = torch.from_numpy(np.ascontiguousarray(G))
+    return t.pin_memory() if pin and torch.cuda.is_available() else t
+
+
+class BatchedMaxEntResult(object):
+    """Host-side result of one batched run.  Arrays are numpy views of pinned host buffers:
+
+    ``alpha`` [n_alpha] (scaled alpha actually used), ``chi2 / S / Q / probability`` [B, n_alpha],
+    ``n_iter`` [B, n_alpha], ``converged`` [B, n_alpha], ``alpha_index`` [B, 5] (-1 = analyzer not available),
+    ``A_out`` [B, 5, n_omega] (analyzer order = ANALYZER_NAMES), ``zero_elements`` = indices skipped because
+    max|G| < G_threshold (python/maxent_loop.py:174-179).  The full A_alpha(omega) stays on the device in
+    ``device.A`` [B, n_alpha, n_omega] and is copied on demand by ``A(b)``."""
+
+    def __init__(self):
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def A(self, b):
+        return self.device.A[b].cpu().numpy()
+
+    def analyzer(self, name):
+        k = ANALYZER_NAMES.index(name)
+        return dict(alpha_index=self.alpha_index[:, k], A_out=self.A_out[:, k])
+
+    def spectrum(self, b):
+        """Per-spectrum dict with the field names of MaxEntResultData (python/maxent_result.py:181-188)."""
+        d = dict(alpha=self.alpha, chi2=self.chi2[b], S=self.S[b], Q=self.Q[b], probability=self.probability[b],
+                 A=self.A(b), omega=self.omega, n_iter=self.n_iter[b], converged=self.converged[b])
+        d["analyzer_results"] = {n: dict(alpha_index=int(self.alpha_index[b, k]), A_out=self.A_out[b, k])
+                                 for k, n in enumerate(ANALYZER_NAMES) if self.alpha_index[b, k] >= 0}
+        return d
+
+
+class BatchedTauMaxEnt(object):
+    """MaxEnt continuation of a batch G[B, n_tau] sharing tau grid, omega mesh, error model and alpha mesh.
+
+    Parameters mirror MaxEntLoop.__init__ (python/maxent_loop.py:83-94): ``cost_function`` in
+    {'normal', 'plusminus', 'bryan'}, ``probability`` in {None, 'normal'}, ``reduce_singular_space``,
+    ``scale_alpha`` ('Ndata' | number | None), ``G_threshold``."""
+
+    launches_per_step = 3          # mx_project_data, mx_alpha_sweep, mx_analyze
+
+    def __init__(self, cost_function="normal", probability=None, reduce_singular_space=1.e-14,
+                 scale_alpha="Ndata", G_threshold=1.e-10, device=None, svd="jacobi", minimizer=None):
+        if cost_function not in _lib.VARIANTS:
+            raise Exception("unknown cost_function %r for the batched path" % (cost_function,))
+        if probability not in (None, "normal"):
+            raise Exception("unknown probability %r" % (probability,))
+        self.cost_function = cost_function
+        self.probability = probability
+        self.reduce_singular_space = reduce_singular_space
+        self.scale_alpha = scale_alpha
+        self.G_threshold = G_threshold
+        self.device = device
+        self.svd = svd
+        self.minimizer = engine.LMParams() if minimizer is None else minimizer
+        self.omega = HyperbolicOmegaMesh(-10, 10, 100)
+        self.alpha_mesh = LogAlphaMesh(1e-4, 20, 20)
+        self.D = None
+        self.A_init = None
+        self.tau = None
+        self.beta = None
+        self.K = None                     # explicit kernel matrix (DataKernel) or None -> TauKernel(tau, omega, beta)
+        self.err = None
+        self.G = None
+        self.problem = None
+        self.gamma, self.linefit_deg, self.bryan_by_integration = 0.2, 0, False
+
+    # ---- inputs -----------------------------------------------------------------------------------
+    def set_kernel_tau(self, tau, omega=None, beta=None):
+        self.tau = np.asarray(tau, dtype=np.float64)
+        self.beta = float(self.tau[-1] if beta is None else beta)
+        if omega is not None:
+            self.omega = omega if hasattr(omega, "delta") else DataOmegaMesh(omega)
+        self.K = None
+        self.problem = None
+
+    def set_kernel_data(self, K, omega):
+        """DataKernel (python/kernels.py:183-207): K[n_tau, n_omega] verbatim."""
+        self.K = np.asarray(K, dtype=np.float64)
+        self.omega = omega if hasattr(omega, "delta") else DataOmegaMesh(omega)
+        self.problem = None
+
+    def set_alpha_mesh_log(self, alpha_min, alpha_max, n_points):
+        self.alpha_mesh = LogAlphaMesh(alpha_min, alpha_max, n_points)
+
+    def set_G_tau_data(self, tau, G):
+        """tau[n_tau], G[B, n_tau] (python/tau_maxent.py:181-196, batched)."""
+        G = np.asarray(G) if not hasattr(G, "data_ptr") else G
+        if G.shape[-1] != len(tau):
+            raise Exception("tau and G_tau don't have the same length")
+        if self.tau is None or len(self.tau) != len(tau) or np.any(self.tau != np.asarray(tau)):
+            self.set_kernel_tau(tau, None, None)
+        self.G = G
+
+    def set_error(self, err):
+        """Scalar or [n_tau] vector shared by the batch (python/tau_maxent.py:227-251)."""
+        self.err = err
+        self.problem = None
+
+    # ---- run --------------------------------------------------------------------------------------
+    def prepare(self):
+        """Everything that depends on the kernel only (KernelSVD, truncation, layout); cached."""
+        if self.problem is not None:
+            return self.problem
+        import torch
+        if not torch.cuda.is_available():
+            raise _lib.MaxEntLibraryError("maxent_b200 needs a CUDA device (no CPU fallback)")
+        dev = torch.device("cuda" if self.device is None else self.device)
+        lib = _lib.load()
+        omega = self.omega
+        with torch.cuda.device(dev):
+            if self.K is None:
+                if self.tau is None:
+                    raise Exception("no kernel: call set_G_tau_data / set_kernel_tau / set_kernel_data first")
+                t_d = torch.as_tensor(self.tau, device=dev)
+                o_d = torch.as_tensor(np.asarray(omega, dtype=np.float64), device=dev)
+                K = torch.empty((len(self.tau), len(omega)), dtype=torch.float64, device=dev)
+                stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+                _lib.check(lib.mx_tau_kernel(t_d.data_ptr(), o_d.data_ptr(), len(self.tau), len(omega), self.beta,
+                                             K.data_ptr(), stream), "mx_tau_kernel")
+            else:
+                K = torch.as_tensor(self.K, device=dev)
+        if self.err is None:
+            raise Exception("no error set: call set_error")
+        D = FlatDefaultModel(omega).D if self.D is None else (self.D.D if hasattr(self.D, "D") else np.asarray(self.D))
+        self.problem = engine.SharedProblem(K, self.err, D, omega.delta, variant=self.cost_function,
+                                            reduce_singular_space=self.reduce_singular_space, device=dev,
+                                            svd=self.svd, A_init=self.A_init)
+        return self.problem
+
+    def alpha_effective(self):
+        """alpha * scale_alpha (python/maxent_loop.py:216-232)."""
+        a = np.asarray(self.alpha_mesh, dtype=np.float64)
+        if self.scale_alpha is None:
+            return a
+        if isinstance(self.scale_alpha, str):
+            if self.scale_alpha.lower() != "ndata":
+                raise Exception("Unknown value {} for scale_alpha".format(self.scale_alpha))
+            return a * self.prepare().n_tau
+        return a * float(self.scale_alpha)
+
+    def run_device(self, G_dev, want_A=True, want_v=False):
+        """Hot path on device-resident data: returns an engine.SweepResult of device tensors."""
+        prob = self.prepare()
+        return engine.run_sweep(prob, G_dev, self.alpha_effective(), probability=self.probability is not None,
+                                lm=self.minimizer, want_A=want_A, want_v=want_v, gamma=self.gamma,
+                                linefit_deg=self.linefit_deg, bryan_by_integration=self.bryan_by_integration)
+
+    def time_sweep_kernel(self, G_dev):
+        """Milliseconds of the mx_alpha_sweep launch alone (CUDA events on the launching stream)."""
+        prob = self.prepare()
+        return engine.run_sweep(prob, G_dev, self.alpha_effective(), probability=self.probability is not None,
+                                lm=self.minimizer, want_A=True, want_v=False, time_kernel=True)
+
+    def run(self, G=None):
+        """Public call: host G[B, n_tau] in (numpy or pinned tensor), BatchedMaxEntResult (host arrays) out."""
+        import torch
+        G = self.G if G is None else G
+        if G is None:
+            raise Exception("no data: call set_G_tau_data")
+        prob = self.prepare()
+        dev = prob.device
+        Gt = G if torch.is_tensor(G) else torch.from_numpy(np.ascontiguousarray(G, dtype=np.float64))
+        if Gt.dim() == 1:
+            Gt = Gt[None, :]
+        out = BatchedMaxEntResult()
+        out.h2d_bytes = Gt.numel() * 8 if not Gt.is_cuda else 0
+        with torch.cuda.device(dev):
+            G_dev = Gt.to(dev, non_blocking=True)
+            res = self.run_device(G_dev)
+            # spectra below the threshold are not continued by the reference (maxent_loop.py:174-179)
+            small = (G_dev.abs().amax(dim=1) < self.G_threshold) if G_dev.shape[0] else None
+            host = {}
+            n_d2h = 0
+            for name, t in (("chi2", res.chi2), ("S", res.S), ("Q", res.Q), ("probability", res.logp),
+                            ("n_iter", res.n_iter), ("status", res.status), ("alpha_index", res.alpha_index),
+                            ("A_out", res.A_out), ("small", small)):
+                if t is None:
+                    host[name] = None
+                    continue
+                buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                buf.copy_(t, non_blocking=True)
+                n_d2h += t.numel() * t.element_size()
+                host[name] = buf
+            torch.cuda.current_stream(dev).synchronize()
+        out.d2h_bytes = n_d2h
+        out.device = res
+        out.omega = self.omega
+        out.alpha = self.alpha_effective()
+        for name in ("chi2", "S", "Q", "probability", "n_iter", "alpha_index", "A_out"):
+            setattr(out, name, host[name].numpy())
+        out.converged = (host["status"].numpy() & _lib.STATUS_CONVERGED).astype(bool)
+        out.zero_elements = [] if host["small"] is None else np.nonzero(host["small"].numpy())[0].tolist()
+        for b in out.zero_elements:
+            out.A_out[b] = 0.0
+        out.n_sv = prob.n_sv
+        return out
+
+
+def gather_results(out, dst=0):
+    """The one collective of a multi-GPU job: gather the per-rank analyzer outputs on ``dst``
+    (NCCL when the process group is nccl; gloo in the CPU tests).  Returns a dict of concatenated
+    arrays on ``dst`` and None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    backend = dist.get_backend()
+    got = {}
+    for name in ("alpha_index", "chi2", "A_out"):
+        arr = getattr(out, name)
+        t = torch.as_tensor(np.ascontiguousarray(arr))
+        if backend == "nccl":
+            t = t.cuda()
+        sizes = [torch.zeros(1, dtype=torch.int64, device=t.device) for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device))
+        if rank == dst:
+            parts = [torch.empty((int(n),) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device) for n in sizes]
+        else:
+            parts = None
+        # ragged shards: point-to-point gather
+        if rank == dst:
+            for r in range(world):
+                if r == dst:
+                    parts[r].copy_(t)
+                elif parts[r].numel():
+                    dist.recv(parts[r], src=r)
+            got[name] = torch.cat(parts, 0).cpu().numpy()
+        elif t.numel():
+            dist.send(t, dst=dst)
+    return got if rank == dst else None

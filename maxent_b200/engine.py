@@ -144,9 +144,69 @@ class SweepResult(object):
                  "alpha_index", "A_out", "n_sv")
 
 
+def _stream(dev):
+    torch = _torch()
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _dev_f64(x, dev):
+    """Host array / tensor -> contiguous float64 tensor on `dev` (asynchronous when the source is pinned)."""
+    torch = _torch()
+    if torch.is_tensor(x):
+        return x.to(device=dev, dtype=torch.float64, non_blocking=True).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64), device=dev)
+
+
+def _problem_struct(prob, alpha, probability, lm, chi2_factor):
+    return _lib.MxProblem(prob.n_tau, prob.n_omega, prob.n_sv, int(alpha.numel()), _lib.VARIANTS[prob.variant],
+                          int(bool(probability)), float(chi2_factor), _ptr(prob.Vt), _ptr(prob.Qw), _ptr(prob.Q),
+                          _ptr(prob.sqrtw), _ptr(prob.xi), _ptr(prob.D), _ptr(prob.delta), _ptr(alpha),
+                          _ptr(prob.v0), lm.c_struct())
+
+
+def project_data(prob, G):
+    """mx_project_data: gt[B, n_sv] = (sqrt(W) Q)^T G and c0[B] = the part of chi2 outside the kept
+    singular space (NormalChi2.f uses the full kernel, python/functions.py:358-360)."""
+    torch = _torch()
+    dev = prob.device
+    with torch.cuda.device(dev):
+        G = _dev_f64(G, dev)
+        B = int(G.shape[0])
+        alpha = torch.ones((1,), dtype=torch.float64, device=dev)
+        p = _problem_struct(prob, alpha, False, LMParams(), 1.0)
+        gt = torch.empty((B, prob.n_sv), dtype=torch.float64, device=dev)
+        c0 = torch.empty((B,), dtype=torch.float64, device=dev)
+        _lib.check(prob.lib.mx_project_data(ctypes.byref(p), _ptr(G), B, _ptr(gt), _ptr(c0), _stream(dev)),
+                   "mx_project_data")
+    return gt, c0
+
+
+def analyze(alpha, chi2, S, logp, A, gamma=0.2, linefit_deg=0, bryan_by_integration=False, device=None):
+    """mx_analyze on arrays (python/analyzers/*.py): returns alpha_index[B, 5] (int32, -1 = not available)
+    and A_out[B, 5, n_omega] (None if A is None)."""
+    torch = _torch()
+    lib = _lib.load()
+    dev = torch.device("cuda" if device is None else device)
+    if torch.is_tensor(chi2) and chi2.is_cuda:
+        dev = chi2.device
+    with torch.cuda.device(dev):
+        alpha, chi2, S = _dev_f64(alpha, dev), _dev_f64(chi2, dev), _dev_f64(S, dev)
+        logp = None if logp is None else _dev_f64(logp, dev)
+        A = None if A is None else _dev_f64(A, dev)
+        B, n_alpha = int(chi2.shape[0]), int(chi2.shape[1])
+        n_omega = int(A.shape[2]) if A is not None else 0
+        idx = torch.full((B, _lib.N_ANALYZERS), -1, dtype=torch.int32, device=dev)
+        A_out = torch.empty((B, _lib.N_ANALYZERS, n_omega), dtype=torch.float64, device=dev) if A is not None else None
+        _lib.check(lib.mx_analyze(_ptr(alpha), _ptr(chi2), _ptr(S), _ptr(logp), _ptr(A), B, n_alpha, n_omega,
+                                  float(gamma), int(linefit_deg), int(bool(bryan_by_integration)),
+                                  _ptr(idx), _ptr(A_out), _stream(dev)), "mx_analyze")
+    return idx, A_out
+
+
 def run_sweep(prob, G, alpha_eff, probability=False, lm=None, chi2_factor=1.0, want_A=True, want_v=True,
-              analyze=True, gamma=0.2, linefit_deg=0, bryan_by_integration=False):
+              analyze_results=True, gamma=0.2, linefit_deg=0, bryan_by_integration=False, time_kernel=False):
     """Fused alpha sweep for a batch G[B, n_tau] sharing `prob`.  `alpha_eff` = alpha * scale_alpha, descending.
+    G may live on the host (numpy / pinned tensor: copied asynchronously) or on the device.
     Everything stays on the device; returns a SweepResult of torch tensors."""
     torch = _torch()
     lib = prob.lib
@@ -154,19 +214,16 @@ def run_sweep(prob, G, alpha_eff, probability=False, lm=None, chi2_factor=1.0, w
     f64, i32 = torch.float64, torch.int32
     lm = LMParams() if lm is None else lm
     with torch.cuda.device(dev):
-        G = torch.as_tensor(G, dtype=f64, device=dev)
+        G = _dev_f64(G, dev)
         if G.dim() == 1:
             G = G[None, :]
-        G = G.contiguous()
         B = int(G.shape[0])
         if G.shape[1] != prob.n_tau:
             raise ValueError("G has %d data points, kernel has %d" % (G.shape[1], prob.n_tau))
-        alpha = torch.as_tensor(np.asarray(alpha_eff, dtype=np.float64), dtype=f64, device=dev).contiguous()
+        alpha = _dev_f64(np.asarray(alpha_eff, dtype=np.float64) if not torch.is_tensor(alpha_eff) else alpha_eff, dev)
         n_alpha, s, n_omega = int(alpha.numel()), prob.n_sv, prob.n_omega
-        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        p = _lib.MxProblem(prob.n_tau, n_omega, s, n_alpha, _lib.VARIANTS[prob.variant], int(bool(probability)),
-                           float(chi2_factor), _ptr(prob.Vt), _ptr(prob.Qw), _ptr(prob.Q), _ptr(prob.sqrtw),
-                           _ptr(prob.xi), _ptr(prob.D), _ptr(prob.delta), _ptr(alpha), _ptr(prob.v0), lm.c_struct())
+        stream = _stream(dev)
+        p = _problem_struct(prob, alpha, probability, lm, chi2_factor)
         gt = torch.empty((B, s), dtype=f64, device=dev)
         c0 = torch.empty((B,), dtype=f64, device=dev)
         _lib.check(lib.mx_project_data(ctypes.byref(p), _ptr(G), B, _ptr(gt), _ptr(c0), stream), "mx_project_data")
@@ -186,10 +243,17 @@ def run_sweep(prob, G, alpha_eff, probability=False, lm=None, chi2_factor=1.0, w
         counter = torch.zeros((1,), dtype=i32, device=dev)
         out = _lib.MxSweepOut(_ptr(r.v), _ptr(r.A), _ptr(r.chi2), _ptr(r.S), _ptr(r.Q), _ptr(r.logp),
                               _ptr(r.n_iter), _ptr(r.n_qeval), _ptr(r.n_solve), _ptr(r.status))
+        if time_kernel:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         _lib.check(lib.mx_alpha_sweep(ctypes.byref(p), _ptr(gt), _ptr(c0), B, ctypes.byref(out), _ptr(counter), stream),
                    "mx_alpha_sweep")
+        if time_kernel:
+            ev1.record()
+            ev1.synchronize()
+            return ev0.elapsed_time(ev1)
         r.alpha_index = r.A_out = None
-        if analyze:
+        if analyze_results:
             r.alpha_index = torch.full((B, _lib.N_ANALYZERS), -1, dtype=i32, device=dev)
             r.A_out = torch.empty((B, _lib.N_ANALYZERS, n_omega), dtype=f64, device=dev) if want_A else None
             _lib.check(lib.mx_analyze(_ptr(alpha), _ptr(r.chi2), _ptr(r.S), _ptr(r.logp) if probability else None,

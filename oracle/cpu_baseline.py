@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""Host-CPU baseline of the alpha-sweep hot path.  TEST / MEASUREMENT INFRASTRUCTURE ONLY.
+
+Times ``oracle/maxent_oracle.py`` (the numpy port that is pinned bit-identically to TRIQS/maxent's
+``TauMaxEnt.run``; the Python reference itself cannot travel to the GPU box) on the host cores:
+one spectrum per process, one BLAS thread per process -- the best-throughput configuration found
+for the reference.  Called by ``bench.py`` (``cpu_baseline`` leg and
+``--impl reference``) in a subprocess so that no CUDA context is forked.
+
+    python -m oracle.cpu_baseline --n-tau 2000 --n-omega 1000 --n-alpha 60 --spectra 8 --procs 8
+
+prints one JSON line: {"spectra": n, "wall_s": t, "spectra_per_s": n/t, "cores": procs, ...}.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+for _v in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ[_v] = os.environ.get("MAXENT_CPU_BLAS_THREADS", "1")
+
+import numpy as np  # noqa: E402
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import maxent_oracle as mo  # noqa: E402
+
+_P = {}
+
+
+def bench_inputs(n_tau, n_omega, n_spectra, seed=5, first=0):
+    """The benchmark's synthetic batch (SURVEY.md 8(d) C5 recipe): rows of
+    default_rng(seed).standard_normal((B, n_tau)) as noise on a Gaussian A(omega), mu = 1."""
+    rng = np.random.default_rng(seed)
+    noise = rng.standard_normal((first + n_spectra, n_tau))[first:]
+    return mo.synthetic_problem(n_tau, n_omega, mu=np.ones(n_spectra), noise=noise)
+
+
+def _init(n_tau, n_omega, n_alpha, n_spectra, thr, seed):
+    _P["pr"] = bench_inputs(n_tau, n_omega, n_spectra, seed)
+    _P["mesh"] = mo.log_alpha_mesh(0.01, 2000, n_alpha)
+    _P["thr"] = thr
+
+
+def _one(b):
+    pr = _P["pr"]
+    t0 = time.perf_counter()
+    # fast_d2: the K^T W K setup product through BLAS instead of the reference's einsum
+    # (python/functions.py:372-377) -- identical numbers to rounding, and it only favours the CPU side.
+    out = mo.maxent_loop(pr["K"], pr["G"][b], pr["err"], pr["omega"], _P["mesh"],
+                         reduce_singular_space=_P["thr"], fast_d2=True)
+    an = out["analyzers"]
+    return dict(b=b, wall=time.perf_counter() - t0, n_iter=int(out["n_iter"].sum()), n_qeval=int(out["n_qeval"]),
+                n_solve=int(out["n_solve"]), n_sv=int(out["n_sv"]),
+                linefit=int(an["LineFitAnalyzer"]["alpha_index"]), chi2curv=int(an["Chi2CurvatureAnalyzer"]["alpha_index"]))
+
+
+def run(n_tau, n_omega, n_alpha, spectra, procs, thr=1e-11, seed=5):
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    if procs <= 1:
+        _init(n_tau, n_omega, n_alpha, spectra, thr, seed)
+        rows = [_one(b) for b in range(spectra)]
+    else:
+        with ctx.Pool(procs, initializer=_init, initargs=(n_tau, n_omega, n_alpha, spectra, thr, seed)) as pool:
+            rows = pool.map(_one, range(spectra), chunksize=1)
+    wall = time.perf_counter() - t0
+    return dict(spectra=spectra, wall_s=wall, spectra_per_s=spectra / wall, cores=procs,
+                per_spectrum_s=[round(r["wall"], 3) for r in rows], n_iter=[r["n_iter"] for r in rows],
+                n_qeval=[r["n_qeval"] for r in rows], n_solve=[r["n_solve"] for r in rows], n_sv=rows[0]["n_sv"],
+                linefit=[r["linefit"] for r in rows], chi2curv=[r["chi2curv"] for r in rows],
+                numpy=np.__version__, blas_threads=int(os.environ["OPENBLAS_NUM_THREADS"]),
+                reduce_singular_space=thr)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n-tau", type=int, default=2000)
+    ap.add_argument("--n-omega", type=int, default=1000)
+    ap.add_argument("--n-alpha", type=int, default=60)
+    ap.add_argument("--spectra", type=int, default=0)
+    ap.add_argument("--procs", type=int, default=0)
+    ap.add_argument("--thr", type=float, default=1e-11)
+    a = ap.parse_args()
+    procs = a.procs or (os.cpu_count() or 1)
+    spectra = a.spectra or procs
+    print(json.dumps(run(a.n_tau, a.n_omega, a.n_alpha, spectra, procs, a.thr)))
+
+
+if __name__ == "__main__":
+    main()

@@ -25,7 +25,7 @@ GOLD = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
 
 def run_reference(tm_mod, tau, G, err, omega_pts, alpha_mesh, cost_function="normal", probability=None,
-                  reduce_singular_space=1e-14, extra_analyzers=False):
+                  reduce_singular_space=1e-14, extra_analyzers=False, noise_floor=True):
     """TauMaxEnt run through the reference's public API (python/tau_maxent.py)."""
     m = tm_mod
     kw = dict(cost_function=cost_function, probability=probability,
@@ -53,6 +53,20 @@ def run_reference(tm_mod, tau, G, err, omega_pts, alpha_mesh, cost_function="nor
                 out["ref_idx_" + name] = int(ar["alpha_index"])
             if "A_out" in ar and ar["A_out"] is not None:
                 out["ref_Aout_" + name] = np.array(ar["A_out"])
+    if noise_floor:
+        # The reference's own reproducibility (SURVEY.md section 0.4 / 8(c) tier T4): re-run it with
+        # G * (1 + 1e-15) and record, per alpha, how far its A / chi2 / S move.
+        tm2 = m.TauMaxEnt(**kw)
+        tm2.set_verbosity(m.VerbosityFlags.Quiet)
+        tm2.set_G_tau_data(np.array(tau), np.array(G) * (1.0 + 1.e-15))
+        tm2.omega = m.DataOmegaMesh(np.array(omega_pts))
+        tm2.alpha_mesh = m.DataAlphaMesh(np.array(alpha_mesh))
+        tm2.set_error(err)
+        res2 = tm2.run()
+        A1, A2 = np.array(res.A), np.array(res2.A)
+        out["noise_A"] = np.max(np.abs(A1 - A2), axis=1) / np.max(np.abs(A1), axis=1)
+        out["noise_chi2"] = np.abs(np.array(res2.chi2) / np.array(res.chi2) - 1.0)
+        out["noise_S"] = np.abs(np.array(res2.S) / np.array(res.S) - 1.0)
     return out, tm, res
 
 

@@ -1,0 +1,97 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports every symbol
+include/maxent_b200.h declares, and the ctypes mirrors of the structs have the C layout.
+No compute calls (there is no GPU here)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "maxent_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from maxent_b200 import _lib, build
+    build.build()
+    return _lib.load()
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"^\s*(?:const\s+)?[A-Za-z_][A-Za-z0-9_]*\s*\*?\s+\*?(mx_[a-z_A-Z0-9]+)\s*\(", src, flags=re.M)
+    return sorted(set(names))
+
+
+def test_header_functions_are_exported(lib):
+    from maxent_b200 import _lib
+    declared = _declared_functions()
+    assert len(declared) >= 10
+    bound = sorted(n for n, _, _ in _lib.SYMBOLS)
+    assert declared == bound, "ctypes table and header disagree"
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_struct_layout_matches_c(tmp_path):
+    """Compile a probe against the header with gcc and compare sizeof/offsetof with the ctypes mirrors."""
+    from maxent_b200 import _lib
+    structs = {"MxLMParams": _lib.MxLMParams, "MxProblem": _lib.MxProblem, "MxSweepOut": _lib.MxSweepOut}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "maxent_b200.h"', 'int main(void){']
+    for sname, cls in structs.items():
+        lines.append('printf("%s.sizeof %%zu\\n", sizeof(%s));' % (sname, sname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (sname, fname, sname, fname))
+    lines.append('printf("MX_MAX_NSV %d\\n", MX_MAX_NSV); printf("MX_N_ANALYZERS %d\\n", MX_N_ANALYZERS);')
+    lines.append("return 0;}")
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.check_call(["gcc", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for sname, cls in structs.items():
+        assert int(out[sname + ".sizeof"]) == ctypes.sizeof(cls)
+        for fname, _ in cls._fields_:
+            assert int(out["%s.%s" % (sname, fname)]) == getattr(cls, fname).offset, (sname, fname)
+    assert int(out["MX_MAX_NSV"]) == _lib.MX_MAX_NSV
+    assert int(out["MX_N_ANALYZERS"]) == _lib.N_ANALYZERS
+
+
+def test_introspection_calls_without_gpu(lib):
+    """The two pure-host entry points work without a device; version string names the architecture."""
+    assert b"sm_100a" in lib.mx_version()
+    from maxent_b200 import _lib
+    for s in (8, 32, 47, 52, 64):
+        cfg = _lib.sweep_config(s)
+        assert 1 <= cfg["spectra_per_cta"] <= 8 and cfg["smem_bytes"] <= 227 * 1024
+    n = lib.mx_layout_V_size(1000, 52)
+    assert n == 125 * 7 * 64
+    assert lib.mx_layout_V_size(1000, 0) < 0
+
+
+def test_product_has_no_cpu_fallback():
+    """The product package never imports the oracle, and computing without a GPU raises."""
+    pkg = os.path.join(ROOT, "maxent_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f
+    import torch
+    if not torch.cuda.is_available():
+        import numpy as np
+        from maxent_b200 import engine, _lib
+        with pytest.raises(_lib.MaxEntLibraryError):
+            engine.SharedProblem(np.eye(4), 1.0, np.ones(4), np.ones(4))
+
+
+def test_missing_library_is_loud(monkeypatch):
+    from maxent_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libmaxent_b200.so")
+    with pytest.raises(_lib.MaxEntLibraryError):
+        _lib.load()

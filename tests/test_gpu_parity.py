@@ -1,0 +1,296 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path, called through the C ABI
+(ctypes -> libmaxent_b200.so), against
+
+* the fixtures the REAL reference produced (tests/golden/*.npz),
+* the CPU oracle run live on small seeded problems,
+* size-independent properties at BASELINE.json's full kernel size.
+
+Tolerances are the floating-point contract of SURVEY.md 8(c), written in tests/gpu_common.py:
+1e-8 relative wherever the reference reproduces itself to that level, 10x the reference's own
+measured noise floor elsewhere, analyzer decisions identical."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import maxent_oracle as mo
+from tests import gpu_common as gc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "the gpu tests need a CUDA device"
+    return torch
+
+
+# ----------------------------------------------------------------------------------------------
+# golden fixtures from the real reference
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["g1_semicircular_prob.npz", "g2_synth_200x100.npz", "g3_plusminus_offdiag.npz",
+                                  "g4_bryan_200x100.npz", "g5_config1_cut1e-11.npz",
+                                  "g5b_config1_default_cut.npz"])
+def test_golden_reference_parity(torch_cuda, name):
+    g = gc.load_golden(name)
+    prob, res = gc.run_fixture(g)
+    assert prob.n_sv == int(g["ref_n_sv"])
+    gc.check_against_reference(g, res)
+    assert bool((res.status[0] & 1).all()), "every alpha converged in the reference run"
+
+
+def test_known_answer_probability(torch_cuda):
+    """The reference's literal numbers, test/python/tau_maxent.py:134-135 (6 decimals)."""
+    g = gc.load_golden("g1_semicircular_prob.npz")
+    _, res = gc.run_fixture(g)
+    np.testing.assert_almost_equal(res.logp[0].cpu().numpy(), g["known_probability"], 6)
+
+
+def test_config1_analyzer_picks(torch_cuda):
+    """BASELINE config 1: LineFit 23 / Chi2Curvature 28 / Entropy 42."""
+    g = gc.load_golden("g5_config1_cut1e-11.npz")
+    _, res = gc.run_fixture(g)
+    assert res.alpha_index[0].cpu().numpy()[:3].tolist() == [23, 28, 42]
+
+
+def test_torch_svd_gives_same_spectra(torch_cuda):
+    """A(omega) does not depend on which SVD produced the singular basis."""
+    g = gc.load_golden("g2_synth_200x100.npz")
+    _, r1 = gc.run_fixture(g, svd="jacobi")
+    _, r2 = gc.run_fixture(g, svd="torch")
+    gc.check_against_reference(g, r2)
+    assert r1.alpha_index[0].tolist() == r2.alpha_index[0].tolist()
+
+
+# ----------------------------------------------------------------------------------------------
+# batching
+# ----------------------------------------------------------------------------------------------
+def test_batch_is_bitwise_independent_of_composition(torch_cuda):
+    """A spectrum's result must not depend on which other spectra share its CTA / the batch."""
+    torch = torch_cuda
+    from maxent_b200 import engine
+    pr = mo.synthetic_problem(300, 120, mu=np.linspace(-1.5, 1.5, 37), seed=7)
+    D = mo.flat_default_model(pr["omega"])
+    prob = engine.SharedProblem(pr["K"], pr["err"], D, pr["delta"], reduce_singular_space=1e-11)
+    alpha = mo.log_alpha_mesh(0.01, 2000, 24) * 300
+    full = engine.run_sweep(prob, pr["G"], alpha)
+    sub = [3, 0, 36, 17, 9]
+    part = engine.run_sweep(prob, pr["G"][sub], alpha)
+    for k, b in enumerate(sub):
+        assert torch.equal(full.A[b], part.A[k])
+        assert torch.equal(full.chi2[b], part.chi2[k])
+        assert torch.equal(full.n_iter[b], part.n_iter[k])
+        assert torch.equal(full.alpha_index[b], part.alpha_index[k])
+    again = engine.run_sweep(prob, pr["G"], alpha)
+    assert torch.equal(full.A, again.A) and torch.equal(full.Q, again.Q)
+
+
+@pytest.mark.parametrize("variant", ["normal", "plusminus", "bryan"])
+def test_small_random_batch_vs_oracle(torch_cuda, variant):
+    """Seeded ragged problem (odd sizes, per-point error bars -> whitening rotation) vs the oracle run live."""
+    from maxent_b200 import engine
+    rng = np.random.RandomState(11)
+    n_tau, n_om = 83, 61
+    pr = mo.synthetic_problem(n_tau, n_om, beta=20.0, mu=[0.7, -0.4, 0.0], sigma=1e-3, seed=5)
+    G = pr["G"] if variant != "plusminus" else pr["G"] - pr["G"][::-1] * 0.6
+    err = 1e-3 * (1.0 + 0.5 * rng.rand(n_tau))
+    D = mo.flat_default_model(pr["omega"])
+    mesh = mo.log_alpha_mesh(0.05, 500, 10)
+    prob = engine.SharedProblem(pr["K"], err, D, pr["delta"], variant=variant, reduce_singular_space=1e-10)
+    res = engine.run_sweep(prob, G, mesh * n_tau, probability=(variant == "normal"))
+    for b in range(G.shape[0]):
+        o = mo.maxent_loop(pr["K"], G[b], err, pr["omega"], mesh, variant=variant, probability=(variant == "normal"),
+                           reduce_singular_space=1e-10)
+        o2 = mo.maxent_loop(pr["K"], G[b] * (1 + 1e-15), err, pr["omega"], mesh, variant=variant,
+                            reduce_singular_space=1e-10, analyzers=False)
+        assert prob.n_sv == o["n_sv"]
+        noise = gc.running_max(gc.rel_A(o2["A"], o["A"]))
+        tol = np.maximum(1e-8, 10 * noise)
+        dA = gc.rel_A(res.A[b].cpu().numpy(), o["A"])
+        assert np.all(dA <= tol), (variant, b, dA / tol)
+        nchi = gc.running_max(np.abs(o2["chi2"] / o["chi2"] - 1))
+        assert np.all(np.abs(res.chi2[b].cpu().numpy() / o["chi2"] - 1) <= np.maximum(1e-8, 10 * nchi))
+        idx = res.alpha_index[b].cpu().numpy()
+        for slot, name in enumerate(gc.AN_NAMES[:3]):
+            assert idx[slot] == o["analyzers"][name]["alpha_index"], (variant, b, name)
+        if variant == "normal":
+            p = res.logp[b].cpu().numpy()
+            assert np.all(np.abs(p - o["probability"]) <= 1e-6 * np.abs(o["probability"]))
+            assert idx[3] == o["analyzers"]["ClassicAnalyzer"]["alpha_index"]
+
+
+def test_maxiter_flags_not_converged(torch_cuda):
+    """maxiter reached -> converged False and n_iter == maxiter (levenberg_minimizer.py:155,245; the '!' flag
+    of maxent_loop.py:255)."""
+    from maxent_b200 import engine
+    g = gc.load_golden("g2_synth_200x100.npz")
+    K = mo.tau_kernel(g["tau"], g["omega"], None)
+    D = mo.flat_default_model(g["omega"])
+    prob = engine.SharedProblem(K, g["err"], D, mo.omega_delta(g["omega"]), reduce_singular_space=1e-11)
+    res = engine.run_sweep(prob, g["G"], g["ref_alpha"], lm=engine.LMParams(maxiter=3))
+    o = mo.maxent_loop(K, g["G"], g["err"], g["omega"], g["alpha_mesh"], reduce_singular_space=1e-11, maxiter=3)
+    np.testing.assert_array_equal(res.n_iter[0].cpu().numpy(), o["n_iter"])
+    np.testing.assert_array_equal((res.status[0].cpu().numpy() & 1).astype(bool), o["converged"])
+    assert not o["converged"].all()
+    np.testing.assert_allclose(res.chi2[0].cpu().numpy(), o["chi2"], rtol=1e-7)
+
+
+def test_huge_alpha_returns_default_model(torch_cuda):
+    """test/python/huge_alpha.py:43-50 : alpha -> infinity reproduces D to 1e-6."""
+    from maxent_b200 import engine
+    pr = mo.synthetic_problem(200, 100, seed=3)
+    D = mo.flat_default_model(pr["omega"])
+    prob = engine.SharedProblem(pr["K"], pr["err"], D, pr["delta"], reduce_singular_space=1e-11)
+    res = engine.run_sweep(prob, pr["G"], np.array([1e25, 1e24, 1e23, 1e22, 1e21]))
+    H = res.A[0, 0].cpu().numpy() * pr["delta"]
+    assert np.max(np.abs(H - D)) < 1e-6
+
+
+# ----------------------------------------------------------------------------------------------
+# the small kernels of the ABI
+# ----------------------------------------------------------------------------------------------
+def test_tau_kernel_and_jacobi_svd(torch_cuda):
+    """test/python/tau_kernel.py:27-69 : kernel formula to 1e-15, U S V^T reconstruction to 1e-13."""
+    torch = torch_cuda
+    from maxent_b200 import _lib
+    lib = _lib.load()
+    tau = np.linspace(0, 10, 150)
+    om = mo.hyperbolic_omega_mesh(-5, 5, 70)
+    t_d, o_d = torch.tensor(tau, device="cuda"), torch.tensor(om, device="cuda")
+    K = torch.empty((150, 70), dtype=torch.float64, device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert lib.mx_tau_kernel(t_d.data_ptr(), o_d.data_ptr(), 150, 70, 10.0, K.data_ptr(), st) == 0
+    Kref = mo.tau_kernel(tau, om, 10.0)
+    assert np.max(np.abs(K.cpu().numpy() - Kref)) < 1e-15
+    U = torch.empty((150, 70), dtype=torch.float64, device="cuda")
+    S = torch.empty((70,), dtype=torch.float64, device="cuda")
+    V = torch.empty((70, 70), dtype=torch.float64, device="cuda")
+    work = torch.empty((150 * 70 + 70 * 70 + 70 + 8,), dtype=torch.float64, device="cuda")
+    sw = ctypes.c_int32(0)
+    assert lib.mx_svd_jacobi(K.data_ptr(), 150, 70, U.data_ptr(), S.data_ptr(), V.data_ptr(), work.data_ptr(), 60,
+                             ctypes.byref(sw), st) == 0
+    torch.cuda.synchronize()
+    rec = (U * S) @ V.T
+    assert float((rec - K).abs().max()) < 1e-13
+    Sref = np.linalg.svd(Kref, compute_uv=False)
+    Sg = S.cpu().numpy()
+    assert np.all(np.diff(Sg) <= 0)
+    assert np.max(np.abs(Sg - Sref)) < 1e-14 * Sref[0] * 10
+    lead = int(np.sum(Sref > 1e-10 * Sref[0]))
+    Vl = V[:, :lead]
+    assert float((Vl.T @ Vl - torch.eye(lead, device="cuda", dtype=torch.float64)).abs().max()) < 1e-12
+
+
+def test_project_data(torch_cuda):
+    """chi2 = |Xi y - gt|^2 + c0 must equal NormalChi2.f (functions.py:358-360) for any H."""
+    torch = torch_cuda
+    from maxent_b200 import engine
+    rng = np.random.RandomState(2)
+    pr = mo.synthetic_problem(90, 50, beta=15.0, mu=[0.3, -0.8], sigma=1e-3, seed=4)
+    err = 1e-3 * (1 + rng.rand(90))
+    D = mo.flat_default_model(pr["omega"])
+    prob = engine.SharedProblem(pr["K"], err, D, pr["delta"], reduce_singular_space=1e-10)
+    G = torch.tensor(pr["G"], device="cuda")
+    gt, c0 = engine.project_data(prob, G)
+    H = torch.tensor(D * np.exp(rng.randn(50) * 0.1), device="cuda")
+    y = prob.Vp.T @ H
+    for b in range(2):
+        chi2 = float(((prob.xi * y - gt[b]) ** 2).sum() + c0[b])
+        # H restricted to the kept singular space: K_s = U S V^T
+        Ks = (prob.U * prob.S) @ prob.V.T
+        ref = float((((Ks @ H - G[b]) / torch.tensor(err, device="cuda")) ** 2).sum())
+        assert abs(chi2 / ref - 1) < 1e-11
+
+
+def test_analyzers_vs_oracle_on_mock_results(torch_cuda):
+    """test/python/analyzers.py:31-46 recipe: analyzers on arrays injected into a result (incl. NaNs,
+    linefit_deg=1, Bryan averaged by integration) vs the oracle's restatement of python/analyzers/*.py."""
+    torch = torch_cuda
+    from maxent_b200 import engine
+    rng = np.random.RandomState(0)
+    n_alpha, n_om, B = 30, 17, 6
+    alpha = mo.log_alpha_mesh(1e-2, 1e3, n_alpha) * 50
+    la = np.log(alpha)
+    chi2 = np.exp(np.where(la[None, :] > 3.0 + rng.rand(B, 1), 2.0 + 1.3 * (la[None, :] - 3.0), 2.0)
+                  + 0.05 * rng.rand(B, n_alpha))
+    S = -np.exp(0.3 * (8 - la))[None, :] * (1 + 0.1 * rng.rand(B, n_alpha))
+    logp = -0.5 * (la[None, :] - 2.0 - rng.rand(B, 1)) ** 2 * 3 + rng.rand(B, n_alpha) * 0.1
+    logp[1, 4] = np.nan
+    logp[2, :] = np.nan
+    A = rng.rand(B, n_alpha, n_om)
+    for deg, integ in ((0, False), (1, True)):
+        idx, Aout = engine.analyze(alpha, chi2, S, logp, A, linefit_deg=deg, bryan_by_integration=integ)
+        idx, Aout = idx.cpu().numpy(), Aout.cpu().numpy()
+        for b in range(B):
+            lf = mo.analyze_linefit(alpha, chi2[b], A[b], deg)
+            assert idx[b, 0] == lf["alpha_index"]
+            assert idx[b, 1] == mo.analyze_chi2_curvature(alpha, chi2[b], A[b])["alpha_index"]
+            assert idx[b, 2] == mo.analyze_entropy(alpha, S[b], A[b])["alpha_index"]
+            assert idx[b, 3] == mo.analyze_classic(alpha, logp[b], A[b])["alpha_index"]
+            br = mo.analyze_bryan(alpha, logp[b], A[b], integ)
+            if br["A_out"] is None:
+                assert idx[b, 4] == -1 and np.all(np.isnan(Aout[b, 4]))
+            else:
+                np.testing.assert_allclose(Aout[b, 4], br["A_out"], rtol=1e-12, atol=1e-14)
+            np.testing.assert_array_equal(Aout[b, 0], A[b, idx[b, 0]])
+
+
+def test_edge_cases(torch_cuda):
+    """Empty batch, n_sv beyond the fused path, bad nu."""
+    torch = torch_cuda
+    from maxent_b200 import engine, _lib
+    pr = mo.synthetic_problem(60, 40, seed=1)
+    D = mo.flat_default_model(pr["omega"])
+    prob = engine.SharedProblem(pr["K"], pr["err"], D, pr["delta"], reduce_singular_space=1e-11)
+    res = engine.run_sweep(prob, np.zeros((0, 60)), np.array([10.0, 1.0]))
+    assert res.A.shape == (0, 2, 40) and res.alpha_index.shape == (0, 5)
+    with pytest.raises(Exception):
+        engine.LMParams(nu=1.0)
+    lib = _lib.load()
+    assert lib.mx_layout_V_size(40, _lib.MX_MAX_NSV + 1) < 0
+    t, sm, th = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    assert lib.mx_sweep_config(_lib.MX_MAX_NSV + 1, ctypes.byref(t), ctypes.byref(sm), ctypes.byref(th)) == -2
+
+
+# ----------------------------------------------------------------------------------------------
+# full-size properties (BASELINE configs 3/5 kernel size: n_tau=2000, n_omega=1000, 60 alphas)
+# ----------------------------------------------------------------------------------------------
+def test_full_size_properties(torch_cuda):
+    """Size-independent checks at the benchmark shape on a 2-wave batch: (1) chi2 and S reported by the
+    kernel equal the values recomputed from A with the FULL kernel matrix (functions.py:358-360,508-510);
+    (2) every converged solution is a stationary point: max|dQ/dv| < 1e-4 (levenberg_minimizer.py:103-106);
+    (3) all spectra are bootstrap copies of one A(omega) -> LineFit/Chi2Curvature picks agree with the
+    reference's (23 / 28) within one mesh point; (4) chi2(alpha) is monotone in alpha."""
+    torch = torch_cuda
+    from maxent_b200 import engine
+    n_tau, n_om, n_alpha, B = 2000, 1000, 60, 300
+    noise = np.random.default_rng(5).standard_normal((B, n_tau))
+    pr = mo.synthetic_problem(n_tau, n_om, mu=np.ones(B), noise=noise)
+    D = mo.flat_default_model(pr["omega"])
+    prob = engine.SharedProblem(pr["K"], pr["err"], D, pr["delta"], reduce_singular_space=1e-11)
+    assert 49 <= prob.n_sv <= 56
+    alpha = mo.log_alpha_mesh(0.01, 2000, n_alpha) * n_tau
+    res = engine.run_sweep(prob, pr["G"], alpha)
+    torch.cuda.synchronize()
+    assert bool((res.status & 1).all())
+    K = torch.tensor(pr["K"], device="cuda")
+    G = torch.tensor(pr["G"], device="cuda")
+    delta = torch.tensor(pr["delta"], device="cuda")
+    Dd = torch.tensor(D, device="cuda")
+    al = torch.tensor(alpha, device="cuda")
+    H = res.A * delta                                             # [B, n_alpha, n_omega]
+    r = (torch.einsum("to,bao->bat", K, H) - G[:, None, :]) / pr["err"]
+    chi2 = (r * r).sum(-1)
+    assert float((chi2 / res.chi2 - 1).abs().max()) < 1e-9
+    S = (H - Dd - H * torch.log(H / Dd)).sum(-1)
+    assert float((S / res.S - 1).abs().max()) < 1e-10
+    # stationarity in the singular space of the kernel: f = V^T diag(H) (K^T W r + alpha log(H/D))
+    dQdH = torch.einsum("bat,to->bao", r / pr["err"], K) + al[None, :, None] * torch.log(H / Dd)
+    f = torch.einsum("os,bao->bas", prob.V, H * dQdH)
+    assert float(f.abs().max()) < 1.05e-4
+    assert bool((res.chi2[:, 1:] <= res.chi2[:, :-1] * (1 + 1e-9)).all())
+    idx = res.alpha_index.cpu().numpy()
+    assert np.all(np.abs(idx[:, 0] - 23) <= 1) and np.all(np.abs(idx[:, 1] - 28) <= 1)
+    n_it = res.n_iter.sum(1).cpu().numpy()
+    assert 600 < n_it.min() and n_it.max() < 1500          # 763-1196 per spectrum
