@@ -25,7 +25,12 @@ extern "C" {
 #define MX_ERR_CUDA         -3
 #define MX_ERR_NO_DEVICE    -4
 
-#define MX_MAX_NSV         128   /* singular-space dimension the fused path supports */
+#define MX_MAX_NSV          64   /* singular-space dimension the fused path supports */
+
+/* sweep engines (MxProblem.engine) */
+#define MX_ENGINE_AUTO       0   /* = MX_ENGINE_SPECTRUM_CTA */
+#define MX_ENGINE_LOCKSTEP   1   /* several spectra per CTA marched in lock-step rounds (csrc/mx_sweep.cuh)   */
+#define MX_ENGINE_SPECTRUM_CTA 2 /* one spectrum per CTA, speculative damping batches (csrc/mx_sweep2.cuh)    */
 
 /* cost-function variants (python/maxent_loop.py:106-121) */
 #define MX_VARIANT_NORMAL    0   /* MaxEntCostFunction + NormalEntropy + NormalH_of_v   */
@@ -65,6 +70,8 @@ typedef struct {
     int32_t n_alpha;
     int32_t variant;          /* MX_VARIANT_*                                                */
     int32_t want_probability; /* NormalLogProbability (probabilities.py:76-85)               */
+    int32_t engine;           /* MX_ENGINE_*                                                 */
+    int32_t reserved;         /* 0                                                           */
     double  chi2_factor;      /* MaxEntCostFunction chi2_factor (cost_function.py:43-53)     */
     const double* Vt;         /* swizzled tile-major V' written by mx_layout_V               */
     const double* Qw;         /* [n_tau, n_sv]  sqrt(W) Q : g~ = Qw^T G                      */
@@ -123,13 +130,18 @@ int mx_project_data(const MxProblem* p, const double* G /*[B, n_tau]*/, int32_t 
  * (python/minimizers/levenberg_minimizer.py:123-248), the cost functions
  * (python/cost_functions/maxent_cost_function.py:68-165, bryan_cost_function.py:57-128) and
  * NormalLogProbability.f (python/probabilities.py:76-85) for B independent spectra.
- * `work_counter` is one int32 on the device (zeroed by the call).  */
+ * `workspace` is device memory of at least mx_sweep_workspace_bytes(p, B) bytes, 256-byte aligned
+ * (work counter + per-CTA scratch rows); its contents need not be initialised.  */
 int mx_alpha_sweep(const MxProblem* p, const double* gt, const double* c0, int32_t B,
-                   const MxSweepOut* out, int32_t* work_counter, void* stream);
+                   const MxSweepOut* out, void* workspace, int64_t workspace_bytes, void* stream);
 
-/* Dynamic shared memory the sweep kernel will request and spectra per CTA it will use for n_sv
- * (introspection for tests / DESIGN.md). */
-int mx_sweep_config(int32_t n_sv, int32_t* spectra_per_cta, int32_t* smem_bytes, int32_t* threads);
+/* Device workspace mx_alpha_sweep needs for this problem and batch size on the current device (<0: MX_ERR_*). */
+int64_t mx_sweep_workspace_bytes(const MxProblem* p, int32_t B);
+
+/* Introspection for tests / DESIGN.md: engine actually used for (n_sv, engine), spectra marched per CTA,
+ * dynamic shared memory and threads per CTA.  Needs no device. */
+int mx_sweep_config(int32_t n_sv, int32_t engine, int32_t* engine_used, int32_t* spectra_per_cta,
+                    int32_t* smem_bytes, int32_t* threads);
 
 /* Analyzer reductions (python/analyzers/*.py) for B spectra:
  * alpha_index[B, MX_N_ANALYZERS] (-1 = not available), A_out[B, MX_N_ANALYZERS, n_omega]. */

@@ -23,6 +23,7 @@ def _units():
     units = [("mx_api.o", "mx_api.cu", []), ("mx_svd.o", "mx_svd.cu", []), ("mx_dispatch.o", "mx_dispatch.cu", [])]
     for nt in SWEEP_NT:
         units.append(("mx_sweep_nt%d.o" % nt, "mx_sweep_inst.cu", ["-DMX_NT=%d" % nt]))
+        units.append(("mx_sweep2_nt%d.o" % nt, "mx_sweep2_inst.cu", ["-DMX_NT=%d" % nt]))
     return units
 
 

@@ -287,32 +287,54 @@ static int fill_args(const MxProblem* p, SweepArgs& a) {
     return MX_OK;
 }
 
-int mx_sweep_config(int32_t n_sv, int32_t* spectra_per_cta, int32_t* smem_bytes, int32_t* threads) {
+int mx_sweep_config(int32_t n_sv, int32_t engine, int32_t* engine_used, int32_t* spectra_per_cta, int32_t* smem_bytes,
+                    int32_t* threads) {
     SweepArgs a = {};
     a.n_sv = n_sv;
-    int t = 0, sm = 0;
-    const int rc = dispatch_sweep(a, nullptr, true, &t, &sm);
+    a.B = 1;
+    int t = 0, sm = 0, eng = 0;
+    const int rc = dispatch_sweep(a, nullptr, true, engine, &eng, &t, &sm, nullptr);
     if (rc != MX_OK) return rc;
+    if (engine_used) *engine_used = eng;
     if (spectra_per_cta) *spectra_per_cta = t;
     if (smem_bytes) *smem_bytes = sm;
-    if (threads) *threads = NTHREADS;
+    if (threads) *threads = eng == 2 ? 128 : NTHREADS;
     return MX_OK;
 }
 
+static const int64_t WS_HEADER = 256;     // bytes reserved for the work counter in front of the scratch rows
+
+int64_t mx_sweep_workspace_bytes(const MxProblem* p, int32_t B) {
+    if (!p || B < 0) return MX_ERR_BAD_ARG;
+    SweepArgs a = {};
+    a.n_sv = p->n_sv;
+    a.B = B > 0 ? B : 1;
+    int eng = 0, grid = 0;
+    const int rc = dispatch_sweep(a, nullptr, true, p->engine, &eng, nullptr, nullptr, &grid);
+    if (rc != MX_OK) return rc;
+    if (eng != 2) return WS_HEADER;
+    if (grid <= 0) return MX_ERR_NO_DEVICE;
+    return WS_HEADER + 8 * sweep_scratch_doubles(p->n_sv, p->n_omega, p->variant, grid);
+}
+
 int mx_alpha_sweep(const MxProblem* p, const double* gt, const double* c0, int32_t B, const MxSweepOut* out,
-                   int32_t* work_counter, void* stream) {
-    if (!p || !gt || !c0 || !out || !work_counter || B < 0) return MX_ERR_BAD_ARG;
+                   void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!p || !gt || !c0 || !out || !workspace || B < 0) return MX_ERR_BAD_ARG;
     if (!out->chi2 || !out->S || !out->Q) return MX_ERR_BAD_ARG;
     if (B == 0) return MX_OK;
     SweepArgs a = {};
     int rc = fill_args(p, a);
     if (rc != MX_OK) return rc;
+    const int64_t need = mx_sweep_workspace_bytes(p, B);
+    if (need < 0) return (int)need;
+    if (workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return MX_ERR_BAD_ARG;
     a.B = B; a.gt = gt; a.c0 = c0;
     a.o_v = out->v; a.o_A = out->A; a.o_chi2 = out->chi2; a.o_S = out->S; a.o_Q = out->Q; a.o_logp = out->logp;
     a.o_niter = out->n_iter; a.o_nq = out->n_qeval; a.o_ns = out->n_solve; a.o_status = out->status;
-    a.counter = work_counter;
-    if (cudaMemsetAsync(work_counter, 0, sizeof(int), (cudaStream_t)stream) != cudaSuccess) return MX_ERR_CUDA;
-    return dispatch_sweep(a, (cudaStream_t)stream, false, nullptr, nullptr);
+    a.counter = reinterpret_cast<int*>(workspace);
+    a.scratch = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + WS_HEADER);
+    if (cudaMemsetAsync(workspace, 0, WS_HEADER, (cudaStream_t)stream) != cudaSuccess) return MX_ERR_CUDA;
+    return dispatch_sweep(a, (cudaStream_t)stream, false, p->engine, nullptr, nullptr, nullptr, nullptr);
 }
 
 int mx_analyze(const double* alpha, const double* chi2, const double* S, const double* logp, const double* A,

@@ -1,4 +1,4 @@
-// Dispatch of the fused sweep over the compiled (NT, T) instantiations.
+// Dispatch of the fused sweep over the compiled instantiations of the two engines.
 #include "mx_common.cuh"
 namespace mx {
 int sweep_nt4(const SweepArgs&, cudaStream_t, bool, int*, int*);
@@ -6,21 +6,51 @@ int sweep_nt5(const SweepArgs&, cudaStream_t, bool, int*, int*);
 int sweep_nt6(const SweepArgs&, cudaStream_t, bool, int*, int*);
 int sweep_nt7(const SweepArgs&, cudaStream_t, bool, int*, int*);
 int sweep_nt8(const SweepArgs&, cudaStream_t, bool, int*, int*);
+}  // namespace mx
+namespace mx2 {
+int sweep2_nt4(const mx::SweepArgs&, cudaStream_t, bool, int*, int*);
+int sweep2_nt5(const mx::SweepArgs&, cudaStream_t, bool, int*, int*);
+int sweep2_nt6(const mx::SweepArgs&, cudaStream_t, bool, int*, int*);
+int sweep2_nt7(const mx::SweepArgs&, cudaStream_t, bool, int*, int*);
+int sweep2_nt8(const mx::SweepArgs&, cudaStream_t, bool, int*, int*);
+}  // namespace mx2
 
-int dispatch_sweep(SweepArgs& a, cudaStream_t stream, bool query, int* o_t, int* o_smem) {
+namespace mx {
+
+int64_t sweep_scratch_doubles(int n_sv, int n_omega, int variant, int grid) {
+    (void)n_sv;
+    const int64_t rowlen = (int64_t)((n_omega + 7) / 8) * 8;
+    return (int64_t)grid * (variant == MX_VARIANT_PLUSMINUS ? 2 : 1) * 9 * rowlen;
+}
+
+int dispatch_sweep(SweepArgs& a, cudaStream_t stream, bool query, int engine, int* o_engine, int* o_t, int* o_smem, int* o_grid) {
     const int s = a.n_sv;
     if (s < 1) return MX_ERR_BAD_ARG;
     int pk = (s * (s + 1)) / 2;
     pk = (pk + 1) & ~1;
     a.pk = pk;
     const int nt = (s + 7) / 8;
+    if (nt > 8) return MX_ERR_UNSUPPORTED;
+    if (engine == 0) engine = 2;
+    if (o_engine) *o_engine = engine;
+    if (engine == 2) {
+        if (o_t) *o_t = 1;
+        switch (nt) {
+            case 1: case 2: case 3: case 4: return mx2::sweep2_nt4(a, stream, query, o_smem, o_grid);
+            case 5: return mx2::sweep2_nt5(a, stream, query, o_smem, o_grid);
+            case 6: return mx2::sweep2_nt6(a, stream, query, o_smem, o_grid);
+            case 7: return mx2::sweep2_nt7(a, stream, query, o_smem, o_grid);
+            default: return mx2::sweep2_nt8(a, stream, query, o_smem, o_grid);
+        }
+    }
+    if (engine != 1) return MX_ERR_BAD_ARG;
+    if (o_grid) *o_grid = 0;
     switch (nt) {
         case 1: case 2: case 3: case 4: return sweep_nt4(a, stream, query, o_t, o_smem);
         case 5: return sweep_nt5(a, stream, query, o_t, o_smem);
         case 6: return sweep_nt6(a, stream, query, o_t, o_smem);
         case 7: return sweep_nt7(a, stream, query, o_t, o_smem);
-        case 8: return sweep_nt8(a, stream, query, o_t, o_smem);
-        default: return MX_ERR_UNSUPPORTED;
+        default: return sweep_nt8(a, stream, query, o_t, o_smem);
     }
 }
 }  // namespace mx

@@ -1,0 +1,968 @@
+// Fused MaxEnt alpha sweep for sm_100a (B200), second generation ("spectrum per CTA").
+//
+// One 4-warp CTA owns one spectrum at a time (persistent CTAs, atomic work counter, 2 CTAs per SM) and
+// runs the whole alpha mesh for it.  The Levenberg-Marquardt iteration of the reference
+// (levenberg_minimizer.py:123-248) asks for Q(v - dv(mu)) at a chain of damping values
+// mu, 1.3 mu, 1.3^2 mu ... that is decided by comparisons of the Q values.  Instead of evaluating the
+// chain one trial at a time (latency bound), the CTA *speculates*: it plans the next up-to-8 damping
+// values the reference would visit, factorises the 8 shifted Hessians concurrently (one warp per
+// matrix, register-resident DMMA-blocked Cholesky) and evaluates the 8 trial vectors in ONE pass over
+// V' where the 8 trials are the M dimension of the FP64 tensor-core MMA (m8n8k4):
+//     T-pass:  x = V' t_b ; H = D exp(x) ; y_b = V'^T H ; S_b ; w_b -> scratch      (8 trials)
+//     H-pass:  Z = V'^T diag(w) V'                                                   (accepted point)
+// The reference's state machine is then replayed on the tabulated Q values, so the sequence of accepted
+// steps, the damping schedule and all comparisons are exactly those of the reference; speculation only
+// changes WHEN a value is computed.  Every point is evaluated once: the accepted trial's chi2, S, y and
+// w = dH/dx are reused for the next gradient / Hessian (the reference recomputes them), and Z is reused
+// when alpha changes (Z does not depend on alpha).
+//
+// All small dense algebra works on 8x8 tiles in the accumulator ("C") layout of the MMA: lane L
+// (r = L/4, q = L%4) holds T[r][2q], T[r][2q+1].  With the k index of the MMA permuted (k-step e uses
+// columns 2q+e) two C-layout tiles multiply as X Y^T straight from their registers (mma_nt), which
+// gives the Cholesky trailing updates, J = eta Z Lambda Z + alpha Z and f = Z u without any layout
+// conversion.  tools/lane_model.py is the numpy model these routines were derived from.
+//
+// V' streams L2 -> shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier, 4 stages) in the
+// swizzled 8x8-tile layout written by mx_layout_V.
+#pragma once
+#include "mx_common.cuh"
+
+namespace mx2 {
+
+using mx::SweepArgs;
+using mx::dmma;
+using mx::tile_off;
+
+constexpr int NWARP = 4;
+constexpr int NTHR = NWARP * 32;
+constexpr int CH = 4;          // k-tiles (8 omega rows each) per staged chunk = one per warp in the T-pass
+constexpr int NSTAGE = 4;
+constexpr int MAXB = 8;        // trials per batch = M of the MMA
+constexpr int NROWS = 9;       // scratch rows per CTA: 8 trials + 1 carried candidate
+constexpr int ID_NONE = -1, ID_CARRY = 8;
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA bulk copy
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+__device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ double quadreduce(double x) { x += shfl_xor(x, 1); x += shfl_xor(x, 2); return x; }
+__device__ __forceinline__ double colreduce(double x) { x += shfl_xor(x, 4); x += shfl_xor(x, 8); x += shfl_xor(x, 16); return x; }
+__device__ __forceinline__ double warp_sum(double x) { return colreduce(quadreduce(x)); }
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// c += X Y^T for two 8x8 tiles in C layout (k permuted: k-step e uses columns 2q+e)
+__device__ __forceinline__ void mma_nt(double (&c)[2], double x0, double x1, double y0, double y1) {
+    dmma(c, x0, y0);
+    dmma(c, x1, y1);
+}
+
+__host__ __device__ constexpr int tri(int I, int J) { return I * (I + 1) / 2 + J; }
+
+// ------------------------------------------------------------------------------------------
+// shared-memory layout (offsets in doubles)
+// ------------------------------------------------------------------------------------------
+template <int NT>
+struct Lay {
+    static constexpr int SP = 8 * NT;
+    static constexpr int NTRI = NT * (NT + 1) / 2;
+    static constexpr int STAGE_D = CH * NT * 64;
+    static constexpr int o_stage = 0;                              // NSTAGE x STAGE_D ; aliases: Zfull [NT*NT*64], yred [4][8][SP]
+    static constexpr int o_J = o_stage + NSTAGE * STAGE_D;         // NTRI tiles, C layout
+    static constexpr int o_tb = o_J + NTRI * 64;                   // [8][SP] trial vectors t_b = v - dv_b
+    static constexpr int o_dvb = o_tb + MAXB * SP;                 // [8][SP]
+    static constexpr int o_yb = o_dvb + MAXB * SP;                 // [8][SP]
+    static constexpr int o_cdv = o_yb + MAXB * SP;                 // carried candidate: dv, y
+    static constexpr int o_cy = o_cdv + SP;
+    static constexpr int o_v = o_cy + SP;
+    static constexpr int o_f = o_v + SP;
+    static constexpr int o_rhs = o_f + SP;
+    static constexpr int o_u = o_rhs + SP;
+    static constexpr int o_gt = o_u + SP;
+    static constexpr int o_xi = o_gt + SP;
+    static constexpr int o_lam = o_xi + SP;
+    static constexpr int o_ycur = o_lam + SP;
+    static constexpr int o_jd = o_ycur + SP;                       // diagonal of J
+    static constexpr int o_sred = o_jd + SP;                       // [4][8] entropy partials
+    static constexpr int o_ctl = o_sred + 32;                      // Ctl block (128 doubles reserved)
+    static constexpr int o_bar = o_ctl + 128;                      // 2*NSTAGE mbarriers
+    static constexpr int total = o_bar + 2 * NSTAGE;
+    static_assert(NT * NT * 64 <= NSTAGE * STAGE_D, "Zfull must fit in the staging area");
+    static_assert(NWARP * 8 * SP <= NSTAGE * STAGE_D, "yred must fit in the staging area");
+};
+
+enum { PH_FIRST = 0, PH_PUMP, PH_PROBE, PH_WALK, PH_DONE };
+
+struct LM {
+    int phase, dv, dvnew;
+    double mu, Q0, Q1, Q2, nuf;
+};
+
+// control block, lives in shared memory; written by thread 0 (and warp 0), read by all after a barrier
+struct Ctl {
+    LM lm;
+    double alpha, c0, chi2_cur, S_cur, Q1cur;
+    double bmu[MAXB];          // damping of every table entry of the current batch
+    double umu[MAXB];          // damping of the unique trials
+    double uQ[NROWS], uchi2[NROWS], uS[NROWS];   // per unique trial (index 8 = carried candidate)
+    double maxf;
+    int bslot[MAXB];           // table entry -> unique trial
+    int urow[NROWS];           // scratch row of each unique trial (8 = carried)
+    int ufail[NROWS];
+    int nb, nuniq;
+    int spec, ia, it, nq, ns, dir_up, cur_row, action, conv;
+    unsigned gchunk;           // chunks streamed so far (pipeline phase bookkeeping)
+};
+static_assert(sizeof(Ctl) <= 128 * sizeof(double), "Ctl must fit its reserved block");
+
+// Levenberg-Marquardt damping search of one iteration, levenberg_minimizer.py:190-233, as a resumable
+// machine: `look(mu, kind, Qref, Q, id)` returns false when Q(v - dv(mu)) is not tabulated yet.
+template <class Look>
+__device__ bool lm_run(LM& s, double nu, double max_mu, double eps_nu, Look&& look) {
+    for (;;) {
+        switch (s.phase) {
+            case PH_FIRST: {                                   // dv = solve(J + mu) ; Q1 = Q(v - dv)      (:192-199)
+                double Q; int id;
+                if (!look(s.mu, 0, s.Q0, Q, id)) return false;
+                s.Q1 = Q; s.dv = id; s.phase = PH_PUMP;
+                break;
+            }
+            case PH_PUMP: {                                    // while (Q1 > Q0 or isnan(Q1)) and mu < max_mu   (:203-206)
+                if ((s.Q1 > s.Q0 || isnan(s.Q1)) && s.mu < max_mu) {
+                    const double m2 = s.mu * nu;
+                    double Q; int id;
+                    if (!look(m2, 0, s.Q0, Q, id)) return false;
+                    s.mu = m2; s.Q1 = Q; s.dv = id;
+                    break;
+                }
+                s.phase = PH_PROBE;
+                break;
+            }
+            case PH_PROBE: {                                   // dv2 = solve(J + nu*mu) ; Q2              (:209-224)
+                double Q; int id;
+                if (!look(nu * s.mu, 1, s.Q1, Q, id)) return false;
+                s.Q2 = Q;
+                if (s.Q2 < s.Q1) { s.nuf = nu; s.mu *= nu; s.Q2 = s.Q1; s.dvnew = id; }
+                else { s.nuf = 1.0 / nu; s.mu /= s.nuf; s.dvnew = s.dv; }
+                s.Q1 = INFINITY;
+                s.phase = PH_WALK;
+                break;
+            }
+            case PH_WALK: {                                    // while Q2 < Q1 and mu < max_mu and mu > nu*eps (:226-233)
+                if (s.Q2 < s.Q1 && s.mu < max_mu && s.mu > eps_nu) {
+                    const double m2 = s.mu * s.nuf;
+                    double Q; int id;
+                    if (!look(m2, 2, s.Q2, Q, id)) return false;
+                    s.Q1 = s.Q2; s.dv = s.dvnew; s.mu = m2; s.dvnew = id; s.Q2 = Q;
+                    break;
+                }
+                s.phase = PH_DONE;
+                return true;
+            }
+            default: return true;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// register-resident blocked Cholesky of an (8 NT)^2 SPD matrix held as lower 8x8 tiles in C layout
+// ------------------------------------------------------------------------------------------
+// Panel step for block column JB: right-looking Cholesky of the 8 columns applied to the diagonal tile,
+// the tiles below it and an identity tile E (which becomes U = L_d^{-T}).
+template <int NT, int JB>
+__device__ __forceinline__ void chol_panel(double (&A)[Lay<NT>::NTRI][2], double (&U)[NT][2], bool& ok, double& logdet,
+                                           bool want_logdet, int r, int q, int lane) {
+    double E[2];
+    E[0] = (r == 2 * q) ? 1.0 : 0.0;
+    E[1] = (r == 2 * q + 1) ? 1.0 : 0.0;
+    double(&P0)[2] = A[tri(JB, JB)];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int jq = j >> 1, je = j & 1;
+        const double ajj = shfl(P0[je], 4 * j + jq);
+        if (!(ajj > 0.0)) ok = false;
+        if (want_logdet) logdet += log(ajj);
+        const double rinv = rsqrt(ajj);
+        const bool mine = (q == jq);
+        // scale column j
+#pragma unroll
+        for (int I = JB; I < NT; ++I) { if (mine) A[tri(I, JB)][je] *= rinv; }
+        if (mine) E[je] *= rinv;
+        const double lk0 = shfl(P0[je], 8 * q + jq);           // L_d[2q][j]
+        const double lk1 = shfl(P0[je], 8 * q + 4 + jq);       // L_d[2q+1][j]
+        const bool u0 = (2 * q > j), u1 = (2 * q + 1 > j);
+        const int src = (lane & ~3) | jq;
+#pragma unroll
+        for (int I = JB; I < NT; ++I) {
+            double(&T)[2] = A[tri(I, JB)];
+            const double lij = shfl(T[je], src);
+            if (u0) T[0] = fma(-lij, lk0, T[0]);
+            if (u1) T[1] = fma(-lij, lk1, T[1]);
+        }
+        {
+            const double lij = shfl(E[je], src);
+            if (u0) E[0] = fma(-lij, lk0, E[0]);
+            if (u1) E[1] = fma(-lij, lk1, E[1]);
+        }
+    }
+    if (r < 2 * q) P0[0] = 0.0;
+    if (r < 2 * q + 1) P0[1] = 0.0;
+    U[JB][0] = E[0];
+    U[JB][1] = E[1];
+}
+
+template <int NT, int JB>
+__device__ __forceinline__ void chol_steps(double (&A)[Lay<NT>::NTRI][2], double (&U)[NT][2], bool& ok, double& logdet,
+                                           bool want_logdet, int r, int q, int lane) {
+    if constexpr (JB < NT) {
+        chol_panel<NT, JB>(A, U, ok, logdet, want_logdet, r, q, lane);
+        // trailing update A[I][J] -= L[I][JB] L[J][JB]^T
+#pragma unroll
+        for (int I = JB + 1; I < NT; ++I) {
+            const double n0 = -A[tri(I, JB)][0], n1 = -A[tri(I, JB)][1];
+#pragma unroll
+            for (int J = JB + 1; J <= I; ++J) mma_nt(A[tri(I, J)], n0, n1, A[tri(J, JB)][0], A[tri(J, JB)][1]);
+        }
+        chol_steps<NT, JB + 1>(A, U, ok, logdet, want_logdet, r, q, lane);
+    }
+}
+
+// Solve L L^T x = rhs with the factor in registers.  rhs: shared vector (8 NT); x is returned
+// row-replicated: xr[I] = x[8 I + r] on every lane of row r.
+template <int NT>
+__device__ __forceinline__ void chol_solve(const double (&A)[Lay<NT>::NTRI][2], const double (&U)[NT][2],
+                                           const double* __restrict__ rhs, double (&xr)[NT], int r) {
+    double zc[NT][2];
+#pragma unroll
+    for (int jb = 0; jb < NT; ++jb) {
+        double acc = 0.0;
+#pragma unroll
+        for (int J = 0; J < jb; ++J) acc = fma(A[tri(jb, J)][0], zc[J][0], fma(A[tri(jb, J)][1], zc[J][1], acc));
+        double rr = rhs[8 * jb + r];
+        if (jb > 0) rr -= quadreduce(acc);
+        zc[jb][0] = colreduce(U[jb][0] * rr);
+        zc[jb][1] = colreduce(U[jb][1] * rr);
+    }
+#pragma unroll
+    for (int jb = NT - 1; jb >= 0; --jb) {
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int I = jb + 1; I < NT; ++I) {
+            c0 = fma(A[tri(I, jb)][0], xr[I], c0);
+            c1 = fma(A[tri(I, jb)][1], xr[I], c1);
+        }
+        double z0 = zc[jb][0], z1 = zc[jb][1];
+        if (jb < NT - 1) { z0 -= colreduce(c0); z1 -= colreduce(c1); }
+        xr[jb] = quadreduce(fma(U[jb][0], z0, U[jb][1] * z1));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// H-pass tile ownership: rows of the lower triangle owned by tile-half 0 (the rest belongs to half 1)
+// ------------------------------------------------------------------------------------------
+__host__ __device__ constexpr unsigned rowmask0(int NT) {
+    return NT == 4 ? 0x9u : NT == 5 ? 0x14u : NT == 6 ? 0x30u : NT == 7 ? 0x61u : NT == 8 ? 0xC4u : 0u;
+}
+template <int NT, int TH>
+__host__ __device__ constexpr bool owns(int I) { return (((rowmask0(NT) >> I) & 1u) != 0u) == (TH == 0); }
+template <int NT, int TH>
+__host__ __device__ constexpr int maxrow() {
+    int m = 0;
+    for (int I = 0; I < NT; ++I) if (owns<NT, TH>(I)) m = I;
+    return m;
+}
+
+template <int NT, int TH>
+__device__ __forceinline__ void hpass_ktile(const double* __restrict__ tile0, double w0, double w1, int offY0, int offY1,
+                                            double (&zacc)[Lay<NT>::NTRI][2]) {
+    constexpr int MR = maxrow<NT, TH>();
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const int off = e ? offY1 : offY0;
+        const double we = e ? w1 : w0;
+        double fr[MR + 1];
+#pragma unroll
+        for (int jt = 0; jt <= MR; ++jt) fr[jt] = tile0[jt * 64 + off];
+#pragma unroll
+        for (int I = 0; I <= MR; ++I) {
+            if (owns<NT, TH>(I)) {
+                const double sc = we * fr[I];
+#pragma unroll
+                for (int J = 0; J <= I; ++J) dmma(zacc[tri(I, J)], sc, fr[J]);
+            }
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// V' streaming pipeline: 1-D TMA bulk copies into NSTAGE staging buffers, full/empty mbarriers.
+// Chunks are numbered globally (g) across passes so that the mbarrier phases stay consistent.
+// ------------------------------------------------------------------------------------------
+template <int NT>
+struct Pipe {
+    double* stage0;
+    const double* Vt;
+    uint64_t* full;
+    uint64_t* empty;
+    int tid, lane, n_kt, nch;
+
+    __device__ __forceinline__ void issue(int c, unsigned g) const {      // thread 0 only
+        const int st = g % NSTAGE;
+        const int t0 = c * CH;
+        const int nt = min(CH, n_kt - t0);
+        const uint32_t bytes = (uint32_t)nt * NT * 64 * sizeof(double);
+        mbar_expect_tx(full + st, bytes);
+        bulk_g2s(stage0 + st * Lay<NT>::STAGE_D, Vt + (size_t)t0 * NT * 64, bytes, full + st);
+    }
+    // all threads; the staging area may have been used as scratch (generic proxy) since the last pass
+    __device__ __forceinline__ void begin(unsigned g0) const {
+        __syncthreads();
+        if (tid == 0) {
+            fence_proxy_async();
+            for (int c = 0; c < NSTAGE - 1 && c < nch; ++c) issue(c, g0 + c);
+        }
+    }
+    // wait for chunk c of the pass; thread 0 first tops the pipeline up (the stage of chunk c-1 is refilled)
+    __device__ __forceinline__ const double* wait(int c, unsigned g0) const {
+        const unsigned g = g0 + c;
+        if (tid == 0) {
+            const int cn = c + NSTAGE - 1;
+            if (cn < nch) {
+                if (c >= 1) mbar_wait(empty + (g - 1) % NSTAGE, ((g - 1) / NSTAGE) & 1);
+                issue(cn, g0 + cn);
+            }
+        }
+        __syncwarp();
+        mbar_wait(full + g % NSTAGE, (g / NSTAGE) & 1);
+        return stage0 + (g % NSTAGE) * Lay<NT>::STAGE_D;
+    }
+    __device__ __forceinline__ void release(int c, unsigned g0) const {
+        const unsigned g = g0 + c;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + g % NSTAGE);
+    }
+};
+
+// H-pass body for one tile half: Z_owned += sum_k w_k V'[k, I] V'[k, J] over this warp's k-tiles, then the
+// two k-groups are added in a fixed order into Zfull (all NT x NT tiles, C layout, symmetric fill).
+template <int NT, int TH>
+__device__ __forceinline__ void hpass_body(const Pipe<NT>& pipe, unsigned g0, const double* __restrict__ wrow, int kg,
+                                           int lane, int r, int q, int offY0, int offY1, double* __restrict__ Zf) {
+    constexpr int NTRI = Lay<NT>::NTRI;
+    const int n_kt = pipe.n_kt, nch = pipe.nch;
+    double zacc[NTRI][2];
+#pragma unroll
+    for (int I = 0; I < NT; ++I)
+        if (owns<NT, TH>(I)) {
+#pragma unroll
+            for (int J = 0; J <= I; ++J) { zacc[tri(I, J)][0] = 0.0; zacc[tri(I, J)][1] = 0.0; }
+        }
+    // this warp handles k-tiles (c*CH + kg) and (c*CH + kg + 2) of every chunk; w is prefetched one chunk ahead
+    auto loadw = [&](int kt) -> double2 {
+        if (kt < n_kt) return *reinterpret_cast<const double2*>(wrow + kt * 8 + 2 * q);
+        return make_double2(0.0, 0.0);
+    };
+    double2 wa = loadw(kg), wb = loadw(kg + 2);
+    for (int c = 0; c < nch; ++c) {
+        const double* stage = pipe.wait(c, g0);
+        const double2 wa_n = loadw((c + 1) * CH + kg), wb_n = loadw((c + 1) * CH + kg + 2);
+        const int kt0 = c * CH + kg, kt1 = kt0 + 2;
+        if (kt0 < n_kt) hpass_ktile<NT, TH>(stage + kg * NT * 64, wa.x, wa.y, offY0, offY1, zacc);
+        if (kt1 < n_kt) hpass_ktile<NT, TH>(stage + (kg + 2) * NT * 64, wb.x, wb.y, offY0, offY1, zacc);
+        wa = wa_n; wb = wb_n;
+        pipe.release(c, g0);
+    }
+    __syncthreads();                                       // every warp is done with the staging area
+    if (kg == 0) {
+#pragma unroll
+        for (int I = 0; I < NT; ++I)
+            if (owns<NT, TH>(I)) {
+#pragma unroll
+                for (int J = 0; J <= I; ++J)
+                    *reinterpret_cast<double2*>(Zf + (I * NT + J) * 64 + 2 * lane) = make_double2(zacc[tri(I, J)][0], zacc[tri(I, J)][1]);
+            }
+    }
+    __syncthreads();
+    if (kg == 1) {
+#pragma unroll
+        for (int I = 0; I < NT; ++I)
+            if (owns<NT, TH>(I)) {
+#pragma unroll
+                for (int J = 0; J <= I; ++J) {
+                    double2* p = reinterpret_cast<double2*>(Zf + (I * NT + J) * 64 + 2 * lane);
+                    const double2 o = *p;
+                    const double2 vv = make_double2(o.x + zacc[tri(I, J)][0], o.y + zacc[tri(I, J)][1]);
+                    *p = vv;
+                    if (I != J) {                          // mirror: tile (J, I) = transpose
+                        Zf[(J * NT + I) * 64 + (2 * q) * 8 + r] = vv.x;
+                        Zf[(J * NT + I) * 64 + (2 * q + 1) * 8 + r] = vv.y;
+                    }
+                }
+            }
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NTHR, 2) sweep2_kernel(const SweepArgs a) {
+    using LY = Lay<NT>;
+    constexpr int SP = LY::SP;
+    constexpr int NTRI = LY::NTRI;
+    extern __shared__ __align__(128) double sm[];
+    Ctl& ctl = *reinterpret_cast<Ctl*>(sm + LY::o_ctl);
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(sm + LY::o_bar);
+    uint64_t* bar_empty = bar_full + NSTAGE;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r = lane >> 2, q = lane & 3;
+    const int s = a.n_sv;
+    const double eps_nu = a.nu * 2.220446049250313e-16;
+    const bool pm = a.variant == MX_VARIANT_PLUSMINUS;
+    const bool bryan = a.variant == MX_VARIANT_BRYAN;
+    const int n_kt = a.n_kt;
+    const int nch = (n_kt + CH - 1) / CH;
+    const size_t rowlen = (size_t)n_kt * 8;
+    double* const wscr = a.scratch + (size_t)blockIdx.x * (pm ? 2 : 1) * NROWS * rowlen;   // [NROWS][rowlen] (+ H rows for plusminus)
+    double* const hscr = wscr + (size_t)NROWS * rowlen;
+
+    const int offX = tile_off(r, 2 * q);
+    const int offY0 = tile_off(2 * q + 0, r);
+    const int offY1 = tile_off(2 * q + 1, r);
+
+    if (tid == 0) {
+        for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full + i, 1); mbar_init(bar_empty + i, NWARP); }
+        ctl.gchunk = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    for (int i = tid; i < SP; i += NTHR) {
+        const double x = i < s ? a.xi[i] : 0.0;
+        sm[LY::o_xi + i] = x;
+        sm[LY::o_lam + i] = x * x;
+    }
+    __syncthreads();
+
+    const Pipe<NT> pipe{sm + LY::o_stage, a.Vt, bar_full, bar_empty, tid, lane, n_kt, nch};
+
+    // ---- T-pass: evaluate the cost function at the trial vectors tb[0..7] ---------------------------
+    // Per unique trial u < nuniq: yb[u], uchi2, uS, uQ, and w (and H) rows in scratch.
+    auto tpass = [&]() {
+        const unsigned g0 = ctl.gchunk;
+        const int nuniq = ctl.nuniq;
+        pipe.begin(g0);
+        double tA[NT][2];
+#pragma unroll
+        for (int jt = 0; jt < NT; ++jt) {
+            const double2 tv = *reinterpret_cast<const double2*>(sm + LY::o_tb + r * SP + 8 * jt + 2 * q);
+            tA[jt][0] = tv.x; tA[jt][1] = tv.y;
+        }
+        double yacc[NT][2];
+#pragma unroll
+        for (int jt = 0; jt < NT; ++jt) { yacc[jt][0] = 0.0; yacc[jt][1] = 0.0; }
+        double sacc = 0.0;
+        const bool live = r < nuniq;
+        double* const wrow = wscr + (size_t)(live ? ctl.urow[r] : 0) * rowlen;
+        double* const hrow = hscr + (size_t)(live ? ctl.urow[r] : 0) * rowlen;
+        for (int c = 0; c < nch; ++c) {
+            const double* stage = pipe.wait(c, g0);
+            const int kt = c * CH + warp;
+            if (kt < n_kt) {
+                const double* tile0 = stage + warp * NT * 64;
+                double C0[2] = {0.0, 0.0}, C1[2] = {0.0, 0.0};
+#pragma unroll
+                for (int jt = 0; jt < NT; ++jt) {
+                    const double2 vv = *reinterpret_cast<const double2*>(tile0 + jt * 64 + offX);
+                    dmma(C0, tA[jt][0], vv.x);
+                    dmma(C1, tA[jt][1], vv.y);
+                }
+                double Hv[2], Wv[2];
+                const int k0 = kt * 8 + 2 * q;
+                const double2 Dv = (k0 + 1 < a.n_omega) ? *reinterpret_cast<const double2*>(a.D + k0)
+                                                        : make_double2(k0 < a.n_omega ? a.D[k0] : 0.0, 0.0);
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const double Dk = i ? Dv.y : Dv.x;
+                    const double x = C0[i] + C1[i];
+                    const double ex = exp(x);
+                    double H, W, st_;
+                    if (!pm) {
+                        // H = D e^x ; S += H - D - H log(H/D), safelog clamp at 1e-100  (functions.py:53-56,508-510)
+                        H = Dk * ex; W = H;
+                        const double lg = (ex <= 1e-100) ? -230.25850929940458 : x;
+                        st_ = H - Dk - H * lg;
+                    } else {
+                        // H = D (e^x - e^-x) ; w = D (e^x + e^-x) ; S = S_n(H+) + S_n(H-)   (functions.py:544-564,778-786)
+                        const double em = exp(-x);
+                        const double Hp = Dk * ex, Hm = Dk * em;
+                        H = Hp - Hm; W = Hp + Hm;
+                        const double lp = (ex <= 1e-100) ? -230.25850929940458 : x;
+                        const double lm = (em <= 1e-100) ? -230.25850929940458 : -x;
+                        st_ = (Hp - Dk - Hp * lp) + (Hm - Dk - Hm * lm);
+                    }
+                    if (Dk == 0.0) { H = 0.0; W = 0.0; st_ = 0.0; }   // padded rows
+                    sacc += st_;
+                    Hv[i] = H; Wv[i] = W;
+                }
+                if (live) {
+                    *reinterpret_cast<double2*>(wrow + k0) = make_double2(Wv[0], Wv[1]);
+                    if (pm) *reinterpret_cast<double2*>(hrow + k0) = make_double2(Hv[0], Hv[1]);
+                }
+#pragma unroll
+                for (int jt = 0; jt < NT; ++jt) {
+                    dmma(yacc[jt], Hv[0], tile0[jt * 64 + offY0]);
+                    dmma(yacc[jt], Hv[1], tile0[jt * 64 + offY1]);
+                }
+            }
+            pipe.release(c, g0);
+        }
+        __syncthreads();                                   // staging area is free: reuse as yred[4][8][SP]
+        if (tid == 0) ctl.gchunk = g0 + nch;
+        double* yred = sm + LY::o_stage;
+#pragma unroll
+        for (int jt = 0; jt < NT; ++jt)
+            *reinterpret_cast<double2*>(yred + (warp * 8 + r) * SP + 8 * jt + 2 * q) = make_double2(yacc[jt][0], yacc[jt][1]);
+        {
+            const double sq = quadreduce(sacc);
+            if (q == 0) sm[LY::o_sred + warp * 8 + r] = sq;
+        }
+        __syncthreads();
+        for (int i = tid; i < MAXB * SP; i += NTHR) {
+            const int b = i / SP, j = i - b * SP;
+            sm[LY::o_yb + i] = (yred[(0 * 8 + b) * SP + j] + yred[(1 * 8 + b) * SP + j]) +
+                               (yred[(2 * 8 + b) * SP + j] + yred[(3 * 8 + b) * SP + j]);
+        }
+        __syncthreads();
+        for (int u = warp; u < nuniq; u += NWARP) {        // chi2 = |Xi y - g~|^2 + c0  (functions.py:358-360 in singular space)
+            double c2 = 0.0;
+            for (int i = lane; i < s; i += 32) {
+                const double rr = sm[LY::o_xi + i] * sm[LY::o_yb + u * SP + i] - sm[LY::o_gt + i];
+                c2 = fma(rr, rr, c2);
+            }
+            c2 = warp_sum(c2) + ctl.c0;
+            const double S = (sm[LY::o_sred + u] + sm[LY::o_sred + 8 + u]) + (sm[LY::o_sred + 16 + u] + sm[LY::o_sred + 24 + u]);
+            if (lane == 0) {
+                ctl.uchi2[u] = c2; ctl.uS[u] = S;
+                ctl.uQ[u] = ctl.ufail[u] ? nan("") : 0.5 * c2 * a.eta - ctl.alpha * S;   // maxent_cost_function.py:82
+            }
+        }
+        __syncthreads();
+    };
+
+    // ---- H-pass: Z = V'^T diag(w) V' with w from scratch row `row` -> Zfull (all NT x NT tiles, C layout) ----
+    auto hpass = [&](int row) {
+        const unsigned g0 = ctl.gchunk;
+        pipe.begin(g0);
+        const int kg = warp >> 1, th = warp & 1;
+        const double* wrow = wscr + (size_t)row * rowlen;
+        double* Zf = sm + LY::o_stage;
+        if (th == 0) hpass_body<NT, 0>(pipe, g0, wrow, kg, lane, r, q, offY0, offY1, Zf);
+        else hpass_body<NT, 1>(pipe, g0, wrow, kg, lane, r, q, offY0, offY1, Zf);
+        if (tid == 0) ctl.gchunk = g0 + nch;
+        __syncthreads();
+    };
+
+    // ---- gradient: u = eta Xi (Xi y - g~) + alpha v ; f = Z u (or u for Bryan) ; maxf -------------------
+    auto gradient = [&]() {
+        const double alpha = ctl.alpha;
+        for (int i = tid; i < SP; i += NTHR) {
+            const double xi = sm[LY::o_xi + i];
+            const double rr = xi * sm[LY::o_ycur + i] - sm[LY::o_gt + i];
+            const double u = (i < s) ? a.eta * xi * rr + alpha * sm[LY::o_v + i] : 0.0;
+            sm[LY::o_u + i] = u;
+            if (bryan) {      // f = g + alpha v ; (eta Lambda Z + mu) dv = f  <=>  (eta Z + mu/Lambda) dv = f/Lambda
+                sm[LY::o_f + i] = u;
+                sm[LY::o_rhs + i] = (i < s) ? u / sm[LY::o_lam + i] : 0.0;
+            }
+        }
+        __syncthreads();
+        if (!bryan) {
+            const double* Zf = sm + LY::o_stage;
+            for (int I = warp; I < NT; I += NWARP) {
+                double cf[2] = {0.0, 0.0};
+#pragma unroll
+                for (int K = 0; K < NT; ++K) {
+                    const double2 z = *reinterpret_cast<const double2*>(Zf + (I * NT + K) * 64 + 2 * lane);
+                    const double2 ub = *reinterpret_cast<const double2*>(sm + LY::o_u + 8 * K + 2 * q);
+                    mma_nt(cf, z.x, z.y, ub.x, ub.y);
+                }
+                if (q == 0) { sm[LY::o_f + 8 * I + r] = cf[0]; sm[LY::o_rhs + 8 * I + r] = cf[0]; }
+            }
+            __syncthreads();
+        }
+        if (warp == 0) {
+            double mf = 0.0;
+            for (int i = lane; i < s; i += 32) mf = fmax(mf, fabs(sm[LY::o_f + i]));
+            mf = warp_max(mf);
+            if (lane == 0) ctl.maxf = mf;
+        }
+        __syncthreads();
+    };
+
+    // ---- J = eta Z Lambda Z + alpha Z (lower tiles, C layout) and its diagonal ---------------------------
+    auto form_J = [&]() {
+        const double* Zf = sm + LY::o_stage;
+        const double alpha = ctl.alpha;
+        for (int t = warp; t < NTRI; t += NWARP) {
+            int I = 0;
+            while (tri(I + 1, 0) <= t) ++I;
+            const int J = t - tri(I, 0);
+            double c[2] = {0.0, 0.0};
+            const double2 zij = *reinterpret_cast<const double2*>(Zf + (I * NT + J) * 64 + 2 * lane);
+            if (!bryan) {
+#pragma unroll
+                for (int K = 0; K < NT; ++K) {
+                    const double2 zi = *reinterpret_cast<const double2*>(Zf + (I * NT + K) * 64 + 2 * lane);
+                    const double2 zj = *reinterpret_cast<const double2*>(Zf + (J * NT + K) * 64 + 2 * lane);
+                    const double2 lm = *reinterpret_cast<const double2*>(sm + LY::o_lam + 8 * K + 2 * q);
+                    mma_nt(c, zi.x * lm.x, zi.y * lm.y, zj.x, zj.y);
+                }
+                c[0] = fma(a.eta, c[0], alpha * zij.x);       // maxent_cost_function.py:161-162 in singular space
+                c[1] = fma(a.eta, c[1], alpha * zij.y);
+            } else {
+                c[0] = a.eta * zij.x; c[1] = a.eta * zij.y;
+            }
+            if (I == J) {                                      // padded rows/columns: identity
+                const int i0 = 8 * I + r;
+                if (i0 >= s) { c[0] = (r == 2 * q) ? 1.0 : 0.0; c[1] = (r == 2 * q + 1) ? 1.0 : 0.0; }
+                else { if (8 * J + 2 * q >= s) c[0] = 0.0; if (8 * J + 2 * q + 1 >= s) c[1] = 0.0; }
+                if (r == 2 * q) sm[LY::o_jd + i0] = c[0];
+                if (r == 2 * q + 1) sm[LY::o_jd + i0] = c[1];
+            } else {
+                if (8 * I + r >= s || 8 * J + 2 * q >= s) c[0] = 0.0;
+                if (8 * I + r >= s || 8 * J + 2 * q + 1 >= s) c[1] = 0.0;
+            }
+            *reinterpret_cast<double2*>(sm + LY::o_J + t * 64 + 2 * lane) = make_double2(c[0], c[1]);
+        }
+        __syncthreads();
+    };
+
+    auto shift_of = [&](int i, double mu) -> double { return bryan ? mu / sm[LY::o_lam + i] : mu; };
+
+    // ---- P3: factorise J + shift(mu_u) and solve for every unique trial (one warp per matrix) -------------
+    auto solve_trials = [&]() {
+        const int nuniq = ctl.nuniq;
+        for (int u = warp; u < nuniq; u += NWARP) {
+            const double mu = ctl.umu[u];
+            double A[NTRI][2];
+#pragma unroll
+            for (int t = 0; t < NTRI; ++t) {
+                const double2 v = *reinterpret_cast<const double2*>(sm + LY::o_J + t * 64 + 2 * lane);
+                A[t][0] = v.x; A[t][1] = v.y;
+            }
+#pragma unroll
+            for (int I = 0; I < NT; ++I) {
+                const int i0 = 8 * I + r;
+                if (i0 < s) {
+                    const double sh = shift_of(i0, mu);
+                    if (r == 2 * q) A[tri(I, I)][0] += sh;
+                    if (r == 2 * q + 1) A[tri(I, I)][1] += sh;
+                }
+            }
+            double U[NT][2];
+            bool ok = true;
+            double ld = 0.0;
+            chol_steps<NT, 0>(A, U, ok, ld, false, r, q, lane);
+            ok = __all_sync(0xffffffffu, ok);
+            double xr[NT];
+            chol_solve<NT>(A, U, sm + LY::o_rhs, xr, r);
+            if (q == 0) {
+#pragma unroll
+                for (int I = 0; I < NT; ++I) {
+                    const int i0 = 8 * I + r;
+                    const double dv = ok ? xr[I] : 0.0;
+                    sm[LY::o_dvb + u * SP + i0] = dv;
+                    sm[LY::o_tb + u * SP + i0] = ok ? sm[LY::o_v + i0] - dv : 0.0;
+                }
+            }
+            if (lane == 0) ctl.ufail[u] = ok ? 0 : 1;
+        }
+        __syncthreads();
+    };
+
+    // ---- log det(I + eta Xi Z Xi / alpha) by warp 0 (probabilities.py:76-85 via Sylvester) -----------------
+    auto logdet_prob = [&]() -> double {       // warp 0 only; returns NaN on a failed factorisation
+        const double* Zf = sm + LY::o_stage;
+        double A[NTRI][2];
+#pragma unroll
+        for (int I = 0; I < NT; ++I) {
+#pragma unroll
+            for (int J = 0; J <= I; ++J) {
+                const double2 z = *reinterpret_cast<const double2*>(Zf + (I * NT + J) * 64 + 2 * lane);
+                const int i0 = 8 * I + r, j0 = 8 * J + 2 * q;
+                const double xi_i = sm[LY::o_xi + i0];
+                double m0 = a.eta * xi_i * z.x * sm[LY::o_xi + j0] / ctl.alpha;
+                double m1 = a.eta * xi_i * z.y * sm[LY::o_xi + j0 + 1] / ctl.alpha;
+                if (i0 >= s || j0 >= s) m0 = 0.0;
+                if (i0 >= s || j0 + 1 >= s) m1 = 0.0;
+                if (i0 == j0) m0 += 1.0;
+                if (i0 == j0 + 1) m1 += 1.0;
+                A[tri(I, J)][0] = m0; A[tri(I, J)][1] = m1;
+            }
+        }
+        double U[NT][2];
+        bool ok = true;
+        double ld = 0.0;
+        chol_steps<NT, 0>(A, U, ok, ld, true, r, q, lane);
+        ok = __all_sync(0xffffffffu, ok);
+        return ok ? ld : nan("");
+    };
+
+    // ==========================================================================================
+    // main loop over spectra
+    // ==========================================================================================
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) ctl.spec = atomicAdd(a.counter, 1);
+        __syncthreads();
+        const int sp = ctl.spec;
+        if (sp >= a.B) break;
+        for (int i = tid; i < SP; i += NTHR) {
+            const double v0 = i < s ? a.v0[i] : 0.0;
+            sm[LY::o_v + i] = v0;
+            sm[LY::o_gt + i] = i < s ? a.gt[(size_t)sp * s + i] : 0.0;
+        }
+        for (int i = tid; i < MAXB * SP; i += NTHR) {
+            const int b = i / SP, j = i - b * SP;
+            sm[LY::o_tb + i] = (b == 0 && j < s) ? a.v0[j] : 0.0;
+        }
+        if (tid == 0) {
+            ctl.ia = 0; ctl.it = 0; ctl.nq = 0; ctl.ns = 0; ctl.dir_up = 1;
+            ctl.alpha = a.alpha[0]; ctl.c0 = a.c0[sp];
+            ctl.lm.mu = a.mu0; ctl.lm.Q0 = nan(""); ctl.lm.phase = PH_FIRST;
+            ctl.nuniq = 1; ctl.nb = 0; ctl.urow[0] = 0; ctl.ufail[0] = 0;
+        }
+        __syncthreads();
+        // first evaluation at v0 (the reference's func_val = function(v), levenberg_minimizer.py:150)
+        tpass();
+        for (int i = tid; i < SP; i += NTHR) sm[LY::o_ycur + i] = sm[LY::o_yb + i];
+        if (tid == 0) { ctl.chi2_cur = ctl.uchi2[0]; ctl.S_cur = ctl.uS[0]; ctl.cur_row = ctl.urow[0]; ctl.nq = 1; }
+        __syncthreads();
+
+        bool spectrum_done = false;
+        while (!spectrum_done) {
+            hpass(ctl.cur_row);
+            // ---- convergence test / alpha loop (levenberg_minimizer.py:157-174, maxent_loop.py:241-266) ----
+            for (;;) {
+                gradient();
+                if (tid == 0) {
+                    LM& L = ctl.lm;
+                    L.Q1 = 0.5 * ctl.chi2_cur * a.eta - ctl.alpha * ctl.S_cur;
+                    // MaxDerivative(1e-4) | RelativeFunctionChange(1e-16)   (levenberg_minimizer.py:103-106)
+                    const bool conv = (ctl.maxf < a.conv_maxd) || (fabs(fabs(L.Q0 - L.Q1) / L.Q1) < a.conv_relq);
+                    ctl.conv = conv ? 1 : 0;
+                    ctl.action = ((conv && ctl.it >= a.miniter) || ctl.it >= a.maxiter) ? 1 : 0;
+                }
+                __syncthreads();
+                if (!ctl.action) break;
+                // ---- this alpha is finished: probability, outputs ----
+                const size_t o = (size_t)sp * a.n_alpha + ctl.ia;
+                if (warp == 0) {
+                    double logp = nan("");
+                    if (a.want_prob) {
+                        const double ld = logdet_prob();
+                        logp = -0.5 * ld - ctl.lm.Q1 - log(ctl.alpha);
+                    }
+                    if (lane == 0) {
+                        const bool hit_max = ctl.it >= a.maxiter;
+                        a.o_chi2[o] = ctl.chi2_cur;
+                        a.o_S[o] = ctl.S_cur;
+                        a.o_Q[o] = ctl.lm.Q1;
+                        if (a.o_logp) a.o_logp[o] = logp;
+                        if (a.o_niter) a.o_niter[o] = hit_max ? a.maxiter : ctl.it + 1;
+                        if (a.o_nq) a.o_nq[o] = ctl.nq;
+                        if (a.o_ns) a.o_ns[o] = ctl.ns;
+                        if (a.o_status) a.o_status[o] = (!hit_max && ctl.conv) ? MX_STATUS_CONVERGED : 0;
+                    }
+                }
+                if (a.o_v) for (int i = tid; i < s; i += NTHR) a.o_v[o * s + i] = sm[LY::o_v + i];
+                if (a.o_A) {                                   // A = H / delta  (functions.py:947-952)
+                    const double* hr = (pm ? hscr : wscr) + (size_t)ctl.cur_row * rowlen;
+                    for (int k = tid; k < a.n_omega; k += NTHR) a.o_A[o * a.n_omega + k] = hr[k] / a.delta[k];
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    ctl.ia++;
+                    if (ctl.ia < a.n_alpha) {
+                        ctl.alpha = a.alpha[ctl.ia];
+                        ctl.lm.mu = a.mu0; ctl.lm.Q0 = nan(""); ctl.it = 0; ctl.nq = 1; ctl.ns = 0; ctl.dir_up = 1;
+                    }
+                }
+                __syncthreads();
+                if (ctl.ia >= a.n_alpha) { spectrum_done = true; break; }
+            }
+            if (spectrum_done) break;
+            form_J();
+            // ---- one Levenberg iteration: speculative batches until the damping search is decided ----
+            if (tid == 0) { ctl.lm.Q0 = ctl.lm.Q1; ctl.lm.phase = PH_FIRST; ctl.nb = 0; ctl.nuniq = 0; ctl.urow[ID_CARRY] = -1; }
+            __syncthreads();
+            for (;;) {
+                if (warp == 0) {
+                    int done = 0;
+                    if (lane == 0) {
+                        LM& L = ctl.lm;
+                        auto look_real = [&](double mu, int, double, double& Q, int& id) -> bool {
+                            for (int i = 0; i < ctl.nb; ++i)
+                                if (ctl.bmu[i] == mu) {
+                                    id = ctl.bslot[i]; Q = ctl.uQ[id];
+                                    ctl.ns++; if (!ctl.ufail[id]) ctl.nq++;
+                                    return true;
+                                }
+                            return false;
+                        };
+                        done = lm_run(L, a.nu, a.max_mu, eps_nu, look_real) ? 1 : 0;
+                        if (!done) {
+                            // carry the live candidate of the old batch (its dv, y, chi2, S and scratch row)
+                            int live = (L.phase == PH_WALK) ? L.dvnew : (L.phase == PH_PROBE ? L.dv : ID_NONE);
+                            if (live >= 0 && live < MAXB) {
+                                ctl.action = live;               // vectors are copied by the whole warp below
+                                ctl.uQ[ID_CARRY] = ctl.uQ[live]; ctl.uchi2[ID_CARRY] = ctl.uchi2[live]; ctl.uS[ID_CARRY] = ctl.uS[live];
+                                ctl.ufail[ID_CARRY] = ctl.ufail[live]; ctl.urow[ID_CARRY] = ctl.urow[live];
+                                if (L.phase == PH_WALK) L.dvnew = ID_CARRY; else L.dv = ID_CARRY;
+                            } else {
+                                ctl.action = -1;
+                                if (live == ID_NONE) ctl.urow[ID_CARRY] = -1;
+                            }
+                            // plan: continue a copy of the machine with pretended outcomes to list the next dampings
+                            LM P = L;
+                            int nn = 0;
+                            double nmu[MAXB], nq_[MAXB];
+                            const bool dir_up = ctl.dir_up != 0;
+                            auto look_plan = [&](double mu, int kind, double Qref, double& Q, int& id) -> bool {
+                                for (int i = 0; i < nn; ++i) if (nmu[i] == mu) { Q = nq_[i]; id = 100 + i; return true; }
+                                if (nn == MAXB) return false;
+                                double pq;
+                                if (kind == 0) pq = isnan(Qref) ? 0.0 : Qref;
+                                else if (kind == 1) pq = dir_up ? Qref - (1.0 + fabs(Qref)) : Qref;
+                                else pq = Qref - (1.0 + fabs(Qref));
+                                nmu[nn] = mu; nq_[nn] = pq; id = 100 + nn; Q = pq; ++nn;
+                                return true;
+                            };
+                            lm_run(P, a.nu, a.max_mu, eps_nu, look_plan);
+                            ctl.nb = nn;
+                            for (int i = 0; i < nn; ++i) ctl.bmu[i] = nmu[i];
+                        }
+                        ctl.conv = done;
+                    }
+                    __syncwarp();
+                    done = ctl.conv;
+                    if (!done) {
+                        const int live = ctl.action;
+                        if (live >= 0) {
+                            for (int i = lane; i < SP; i += 32) {
+                                sm[LY::o_cdv + i] = sm[LY::o_dvb + live * SP + i];
+                                sm[LY::o_cy + i] = sm[LY::o_yb + live * SP + i];
+                            }
+                        }
+                        // dedup: two dampings whose shifted diagonals are bitwise identical give identical trials
+                        const int nb = ctl.nb;
+                        int nuniq = 0;
+                        int rowp = 0;
+                        for (int i = 0; i < nb; ++i) {
+                            const double mu_i = ctl.bmu[i];
+                            int alias = -1;
+                            for (int u = 0; u < nuniq && alias < 0; ++u) {
+                                const double mu_u = ctl.umu[u];
+                                bool same = true;
+                                for (int k = lane; k < s; k += 32) {
+                                    const double jd = sm[LY::o_jd + k];
+                                    same = same && ((jd + shift_of(k, mu_i)) == (jd + shift_of(k, mu_u)));
+                                }
+                                if (__all_sync(0xffffffffu, same)) alias = u;
+                            }
+                            if (alias < 0) {
+                                alias = nuniq++;
+                                if (rowp == ctl.urow[ID_CARRY]) ++rowp;
+                                if (lane == 0) { ctl.umu[alias] = mu_i; ctl.urow[alias] = rowp; ctl.ufail[alias] = 0; }
+                                ++rowp;
+                            }
+                            if (lane == 0) ctl.bslot[i] = alias;
+                            __syncwarp();
+                        }
+                        if (lane == 0) ctl.nuniq = nuniq;
+                    }
+                }
+                __syncthreads();
+                if (ctl.conv) break;
+                for (int i = tid; i < MAXB * SP; i += NTHR) if (i >= ctl.nuniq * SP) sm[LY::o_tb + i] = 0.0;
+                solve_trials();
+                tpass();
+            }
+            // ---- accept: v -= dv ; the accepted trial becomes the current point (levenberg_minimizer.py:239-243) ----
+            {
+                const int id = ctl.lm.dv;
+                const double* dv = (id == ID_CARRY) ? sm + LY::o_cdv : sm + LY::o_dvb + id * SP;
+                const double* yy = (id == ID_CARRY) ? sm + LY::o_cy : sm + LY::o_yb + id * SP;
+                for (int i = tid; i < SP; i += NTHR) {
+                    if (i < s) sm[LY::o_v + i] -= dv[i];
+                    sm[LY::o_ycur + i] = yy[i];
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    ctl.chi2_cur = ctl.uchi2[id]; ctl.S_cur = ctl.uS[id]; ctl.cur_row = ctl.urow[id];
+                    ctl.it++;
+                    ctl.nq++;                                    // the reference re-evaluates func_val = function(v)
+                    ctl.dir_up = (ctl.lm.nuf == a.nu) ? 1 : 0;
+                }
+                __syncthreads();
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side launch
+// ------------------------------------------------------------------------------------------
+template <int NT>
+int launch_sweep2(const SweepArgs& a, cudaStream_t stream, bool query, int* o_smem, int* o_grid) {
+    const size_t bytes = (size_t)Lay<NT>::total * sizeof(double);
+    if (o_smem) *o_smem = (int)bytes;
+    int dev = 0, sms = 0;
+    if (!query || o_grid) {
+        if (cudaGetDevice(&dev) != cudaSuccess) { if (query) { if (o_grid) *o_grid = 0; return MX_OK; } return MX_ERR_NO_DEVICE; }
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    int grid = 2 * sms;
+    if (grid > a.B) grid = a.B;
+    if (grid < 1) grid = 1;
+    if (o_grid) *o_grid = grid;
+    if (query) return MX_OK;
+    cudaError_t e = cudaFuncSetAttribute(sweep2_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return MX_ERR_CUDA;
+    sweep2_kernel<NT><<<grid, NTHR, bytes, stream>>>(a);
+    return cudaGetLastError() == cudaSuccess ? MX_OK : MX_ERR_CUDA;
+}
+
+}  // namespace mx2

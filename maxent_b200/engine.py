@@ -50,7 +50,7 @@ class SharedProblem(object):
     this rotation because mu*1 is."""
 
     def __init__(self, K, err, D, delta, variant="normal", reduce_singular_space=1.e-14, device=None,
-                 svd="jacobi", A_init=None, max_nsv=None):
+                 svd="jacobi", A_init=None, max_nsv=None, engine=0):
         torch = _torch()
         if not torch.cuda.is_available():
             raise _lib.MaxEntLibraryError("maxent_b200 needs a CUDA device (no CPU fallback)")
@@ -109,7 +109,8 @@ class SharedProblem(object):
             self.Vt = torch.empty(n, dtype=f64, device=dev)
             stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             _lib.check(self.lib.mx_layout_V(_ptr(self.Vp), self.n_omega, s, _ptr(self.Vt), stream), "mx_layout_V")
-            self.config = _lib.sweep_config(s)
+            self.engine = int(engine)
+            self.config = _lib.sweep_config(s, self.engine)
 
     def _svd(self, K, method):
         torch = _torch()
@@ -159,7 +160,7 @@ def _dev_f64(x, dev):
 
 def _problem_struct(prob, alpha, probability, lm, chi2_factor):
     return _lib.MxProblem(prob.n_tau, prob.n_omega, prob.n_sv, int(alpha.numel()), _lib.VARIANTS[prob.variant],
-                          int(bool(probability)), float(chi2_factor), _ptr(prob.Vt), _ptr(prob.Qw), _ptr(prob.Q),
+                          int(bool(probability)), int(getattr(prob, "engine", 0)), 0, float(chi2_factor), _ptr(prob.Vt), _ptr(prob.Qw), _ptr(prob.Q),
                           _ptr(prob.sqrtw), _ptr(prob.xi), _ptr(prob.D), _ptr(prob.delta), _ptr(alpha),
                           _ptr(prob.v0), lm.c_struct())
 
@@ -240,14 +241,19 @@ def run_sweep(prob, G, alpha_eff, probability=False, lm=None, chi2_factor=1.0, w
         r.n_qeval = torch.zeros((B, n_alpha), dtype=i32, device=dev)
         r.n_solve = torch.zeros((B, n_alpha), dtype=i32, device=dev)
         r.status = torch.zeros((B, n_alpha), dtype=i32, device=dev)
-        counter = torch.zeros((1,), dtype=i32, device=dev)
+        ws_bytes = int(lib.mx_sweep_workspace_bytes(ctypes.byref(p), B))
+        if ws_bytes < 0:
+            _lib.check(ws_bytes, "mx_sweep_workspace_bytes")
+        ws = getattr(prob, "_workspace", None)
+        if ws is None or ws.numel() < ws_bytes:
+            ws = prob._workspace = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         out = _lib.MxSweepOut(_ptr(r.v), _ptr(r.A), _ptr(r.chi2), _ptr(r.S), _ptr(r.Q), _ptr(r.logp),
                               _ptr(r.n_iter), _ptr(r.n_qeval), _ptr(r.n_solve), _ptr(r.status))
         if time_kernel:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-        _lib.check(lib.mx_alpha_sweep(ctypes.byref(p), _ptr(gt), _ptr(c0), B, ctypes.byref(out), _ptr(counter), stream),
-                   "mx_alpha_sweep")
+        _lib.check(lib.mx_alpha_sweep(ctypes.byref(p), _ptr(gt), _ptr(c0), B, ctypes.byref(out), _ptr(ws), ws_bytes,
+                                      stream), "mx_alpha_sweep")
         if time_kernel:
             ev1.record()
             ev1.synchronize()

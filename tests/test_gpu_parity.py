@@ -249,8 +249,8 @@ def test_edge_cases(torch_cuda):
         engine.LMParams(nu=1.0)
     lib = _lib.load()
     assert lib.mx_layout_V_size(40, _lib.MX_MAX_NSV + 1) < 0
-    t, sm, th = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
-    assert lib.mx_sweep_config(_lib.MX_MAX_NSV + 1, ctypes.byref(t), ctypes.byref(sm), ctypes.byref(th)) == -2
+    e, t, sm, th = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    assert lib.mx_sweep_config(_lib.MX_MAX_NSV + 1, 0, ctypes.byref(e), ctypes.byref(t), ctypes.byref(sm), ctypes.byref(th)) == -2
 
 
 # ----------------------------------------------------------------------------------------------
