@@ -25,7 +25,7 @@ extern "C" {
 #define MX_ERR_CUDA         -3
 #define MX_ERR_NO_DEVICE    -4
 
-#define MX_MAX_NSV          64   /* singular-space dimension the fused path supports */
+#define MX_MAX_NSV          80   /* singular-space dimension the fused path supports */
 
 /* sweep engines (MxProblem.engine) */
 #define MX_ENGINE_AUTO       0   /* = MX_ENGINE_SPECTRUM_CTA */

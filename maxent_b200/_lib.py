@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmaxent_b200.so")
 
 MX_OK = 0
-MX_MAX_NSV = 64
+MX_MAX_NSV = 80
 ENGINE_AUTO, ENGINE_LOCKSTEP, ENGINE_SPECTRUM_CTA = 0, 1, 2
 VARIANTS = {"normal": 0, "plusminus": 1, "bryan": 2}
 AN_LINEFIT, AN_CHI2CURV, AN_ENTROPY, AN_CLASSIC, AN_BRYAN = range(5)

@@ -16,13 +16,15 @@ LIB = os.path.join(HERE, "libmaxent_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
-SWEEP_NT = (4, 5, 6, 7, 8)
+SWEEP_NT = (4, 5, 6, 7, 8)            # lock-step engine (csrc/mx_sweep.cuh)
+SWEEP2_NT = (4, 5, 6, 7, 8, 9, 10)    # spectrum-per-CTA engine (csrc/mx_sweep2.cuh)
 
 
 def _units():
     units = [("mx_api.o", "mx_api.cu", []), ("mx_svd.o", "mx_svd.cu", []), ("mx_dispatch.o", "mx_dispatch.cu", [])]
     for nt in SWEEP_NT:
         units.append(("mx_sweep_nt%d.o" % nt, "mx_sweep_inst.cu", ["-DMX_NT=%d" % nt]))
+    for nt in SWEEP2_NT:
         units.append(("mx_sweep2_nt%d.o" % nt, "mx_sweep2_inst.cu", ["-DMX_NT=%d" % nt]))
     return units
 

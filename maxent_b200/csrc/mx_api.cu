@@ -2,6 +2,7 @@
 // V' re-tiling, TauKernel fill, data projection, analyzer reductions.
 #include "mx_common.cuh"
 #include <stdio.h>
+#include <stdint.h>
 
 namespace mx {
 
@@ -267,9 +268,9 @@ int mx_svd_jacobi(const double* K, int32_t m, int32_t n, double* U, double* S, d
 }
 
 int mx_project_data(const MxProblem* p, const double* G, int32_t B, double* gt, double* c0, void* stream) {
+    if (B == 0) return MX_OK;
     if (!p || !G || !gt || !c0 || B < 0) return MX_ERR_BAD_ARG;
     if (p->n_sv < 1 || p->n_sv > MX_MAX_NSV) return MX_ERR_UNSUPPORTED;
-    if (B == 0) return MX_OK;
     project_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(p->Qw, p->Qo, p->sqrtw, G, p->n_tau, p->n_sv, gt, c0);
     return cudaGetLastError() == cudaSuccess ? MX_OK : MX_ERR_CUDA;
 }
@@ -319,9 +320,9 @@ int64_t mx_sweep_workspace_bytes(const MxProblem* p, int32_t B) {
 
 int mx_alpha_sweep(const MxProblem* p, const double* gt, const double* c0, int32_t B, const MxSweepOut* out,
                    void* workspace, int64_t workspace_bytes, void* stream) {
+    if (B == 0) return MX_OK;
     if (!p || !gt || !c0 || !out || !workspace || B < 0) return MX_ERR_BAD_ARG;
     if (!out->chi2 || !out->S || !out->Q) return MX_ERR_BAD_ARG;
-    if (B == 0) return MX_OK;
     SweepArgs a = {};
     int rc = fill_args(p, a);
     if (rc != MX_OK) return rc;
@@ -340,8 +341,8 @@ int mx_alpha_sweep(const MxProblem* p, const double* gt, const double* c0, int32
 int mx_analyze(const double* alpha, const double* chi2, const double* S, const double* logp, const double* A,
                int32_t B, int32_t n_alpha, int32_t n_omega, double gamma, int32_t linefit_deg,
                int32_t bryan_by_integration, int32_t* alpha_index, double* A_out, void* stream) {
-    if (!alpha || !chi2 || !S || !alpha_index || B < 0 || n_alpha < 1 || n_alpha > 1024) return MX_ERR_BAD_ARG;
     if (B == 0) return MX_OK;
+    if (!alpha || !chi2 || !S || !alpha_index || B < 0 || n_alpha < 1 || n_alpha > 1024) return MX_ERR_BAD_ARG;
     const size_t shb = 4 * (size_t)n_alpha * sizeof(double);
     analyze_kernel<<<B, 128, shb, (cudaStream_t)stream>>>(alpha, chi2, S, logp, A, n_alpha, n_omega, gamma,
                                                           linefit_deg, bryan_by_integration, alpha_index, A_out);

@@ -13,6 +13,8 @@ int sweep2_nt5(const mx::SweepArgs&, cudaStream_t, bool, int*, int*);
 int sweep2_nt6(const mx::SweepArgs&, cudaStream_t, bool, int*, int*);
 int sweep2_nt7(const mx::SweepArgs&, cudaStream_t, bool, int*, int*);
 int sweep2_nt8(const mx::SweepArgs&, cudaStream_t, bool, int*, int*);
+int sweep2_nt9(const mx::SweepArgs&, cudaStream_t, bool, int*, int*);
+int sweep2_nt10(const mx::SweepArgs&, cudaStream_t, bool, int*, int*);
 }  // namespace mx2
 
 namespace mx {
@@ -30,8 +32,9 @@ int dispatch_sweep(SweepArgs& a, cudaStream_t stream, bool query, int engine, in
     pk = (pk + 1) & ~1;
     a.pk = pk;
     const int nt = (s + 7) / 8;
-    if (nt > 8) return MX_ERR_UNSUPPORTED;
+    if (nt > 10) return MX_ERR_UNSUPPORTED;
     if (engine == 0) engine = 2;
+    if (engine == 1 && nt > 8) return MX_ERR_UNSUPPORTED;
     if (o_engine) *o_engine = engine;
     if (engine == 2) {
         if (o_t) *o_t = 1;
@@ -40,7 +43,9 @@ int dispatch_sweep(SweepArgs& a, cudaStream_t stream, bool query, int engine, in
             case 5: return mx2::sweep2_nt5(a, stream, query, o_smem, o_grid);
             case 6: return mx2::sweep2_nt6(a, stream, query, o_smem, o_grid);
             case 7: return mx2::sweep2_nt7(a, stream, query, o_smem, o_grid);
-            default: return mx2::sweep2_nt8(a, stream, query, o_smem, o_grid);
+            case 8: return mx2::sweep2_nt8(a, stream, query, o_smem, o_grid);
+            case 9: return mx2::sweep2_nt9(a, stream, query, o_smem, o_grid);
+            default: return mx2::sweep2_nt10(a, stream, query, o_smem, o_grid);
         }
     }
     if (engine != 1) return MX_ERR_BAD_ARG;

@@ -37,7 +37,8 @@ constexpr int NWARP = 4;
 constexpr int NTHR = NWARP * 32;
 constexpr int CH = 4;          // k-tiles (8 omega rows each) per staged chunk = one per warp in the T-pass
 constexpr int NSTAGE = 4;
-constexpr int MAXB = 8;        // trials per batch = M of the MMA
+constexpr int MAXB = 8;        // unique trials per batch = M of the MMA
+constexpr int NTAB = 32;       // damping values tabulated per batch (several may share one unique trial)
 constexpr int NROWS = 9;       // scratch rows per CTA: 8 trials + 1 carried candidate
 constexpr int ID_NONE = -1, ID_CARRY = 8;
 
@@ -82,6 +83,19 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
+// 1/sqrt(a) for a > 0: MUFU.RSQ64H seed (about 2^-20) + two Newton steps (quadratic: 2^-40, then rounding level);
+// shorter dependent chain than the library rsqrt(), which sits on the critical path of the Cholesky panel
+__device__ __forceinline__ double rsqrt_nr(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double h = 0.5 * y;
+    double e = fma(-a * y, y, 1.0);
+    y = fma(h, e, y);
+    h = 0.5 * y;
+    e = fma(-a * y, y, 1.0);
+    return fma(h, e, y);
+}
+
 // c += X Y^T for two 8x8 tiles in C layout (k permuted: k-step e uses columns 2q+e)
 __device__ __forceinline__ void mma_nt(double (&c)[2], double x0, double x1, double y0, double y1) {
     dmma(c, x0, y0);
@@ -115,8 +129,8 @@ struct Lay {
     static constexpr int o_ycur = o_lam + SP;
     static constexpr int o_jd = o_ycur + SP;                       // diagonal of J
     static constexpr int o_sred = o_jd + SP;                       // [4][8] entropy partials
-    static constexpr int o_ctl = o_sred + 32;                      // Ctl block (128 doubles reserved)
-    static constexpr int o_bar = o_ctl + 128;                      // 2*NSTAGE mbarriers
+    static constexpr int o_ctl = o_sred + 32;                      // Ctl block (192 doubles reserved)
+    static constexpr int o_bar = o_ctl + 192;                      // 2*NSTAGE mbarriers
     static constexpr int total = o_bar + 2 * NSTAGE;
     static_assert(NT * NT * 64 <= NSTAGE * STAGE_D, "Zfull must fit in the staging area");
     static_assert(NWARP * 8 * SP <= NSTAGE * STAGE_D, "yred must fit in the staging area");
@@ -133,18 +147,19 @@ struct LM {
 struct Ctl {
     LM lm;
     double alpha, c0, chi2_cur, S_cur, Q1cur;
-    double bmu[MAXB];          // damping of every table entry of the current batch
-    double umu[MAXB];          // damping of the unique trials
+    double bmu[NTAB];          // damping of every table entry of the current batch
+    double umu[NROWS];         // damping of the unique trials (index 8 = carried candidate)
     double uQ[NROWS], uchi2[NROWS], uS[NROWS];   // per unique trial (index 8 = carried candidate)
+    double pq[MAXB];           // planning: pretended Q of the planned unique trials
     double maxf;
-    int bslot[MAXB];           // table entry -> unique trial
+    int bslot[NTAB];           // table entry -> unique trial
     int urow[NROWS];           // scratch row of each unique trial (8 = carried)
     int ufail[NROWS];
     int nb, nuniq;
     int spec, ia, it, nq, ns, dir_up, cur_row, action, conv;
     unsigned gchunk;           // chunks streamed so far (pipeline phase bookkeeping)
 };
-static_assert(sizeof(Ctl) <= 128 * sizeof(double), "Ctl must fit its reserved block");
+static_assert(sizeof(Ctl) <= 192 * sizeof(double), "Ctl must fit its reserved block");
 
 // Levenberg-Marquardt damping search of one iteration, levenberg_minimizer.py:190-233, as a resumable
 // machine: `look(mu, kind, Qref, Q, id)` returns false when Q(v - dv(mu)) is not tabulated yet.
@@ -198,8 +213,9 @@ __device__ bool lm_run(LM& s, double nu, double max_mu, double eps_nu, Look&& lo
 // ------------------------------------------------------------------------------------------
 // register-resident blocked Cholesky of an (8 NT)^2 SPD matrix held as lower 8x8 tiles in C layout
 // ------------------------------------------------------------------------------------------
-// Panel step for block column JB: right-looking Cholesky of the 8 columns applied to the diagonal tile,
-// the tiles below it and an identity tile E (which becomes U = L_d^{-T}).
+// Panel step for block column JB: right-looking Cholesky of the diagonal tile together with an identity tile E
+// (which becomes U = L_d^{-T}); the tiles below are then solved with two MMAs each: L[I][JB] = A[I][JB] U =
+// A[I][JB] W^T with W = U^T = L_d^{-1} (in-register transpose of U).
 template <int NT, int JB>
 __device__ __forceinline__ void chol_panel(double (&A)[Lay<NT>::NTRI][2], double (&U)[NT][2], bool& ok, double& logdet,
                                            bool want_logdet, int r, int q, int lane) {
@@ -213,33 +229,35 @@ __device__ __forceinline__ void chol_panel(double (&A)[Lay<NT>::NTRI][2], double
         const double ajj = shfl(P0[je], 4 * j + jq);
         if (!(ajj > 0.0)) ok = false;
         if (want_logdet) logdet += log(ajj);
-        const double rinv = rsqrt(ajj);
-        const bool mine = (q == jq);
-        // scale column j
-#pragma unroll
-        for (int I = JB; I < NT; ++I) { if (mine) A[tri(I, JB)][je] *= rinv; }
-        if (mine) E[je] *= rinv;
-        const double lk0 = shfl(P0[je], 8 * q + jq);           // L_d[2q][j]
-        const double lk1 = shfl(P0[je], 8 * q + 4 + jq);       // L_d[2q+1][j]
+        const double rinv = rsqrt_nr(ajj);
+        if (q == jq) { P0[je] *= rinv; E[je] *= rinv; }          // scale column j
+        const double lk0 = shfl(P0[je], 8 * q + jq);              // L_d[2q][j]
+        const double lk1 = shfl(P0[je], 8 * q + 4 + jq);          // L_d[2q+1][j]
         const bool u0 = (2 * q > j), u1 = (2 * q + 1 > j);
         const int src = (lane & ~3) | jq;
-#pragma unroll
-        for (int I = JB; I < NT; ++I) {
-            double(&T)[2] = A[tri(I, JB)];
-            const double lij = shfl(T[je], src);
-            if (u0) T[0] = fma(-lij, lk0, T[0]);
-            if (u1) T[1] = fma(-lij, lk1, T[1]);
-        }
-        {
-            const double lij = shfl(E[je], src);
-            if (u0) E[0] = fma(-lij, lk0, E[0]);
-            if (u1) E[1] = fma(-lij, lk1, E[1]);
-        }
+        const double lp = shfl(P0[je], src);
+        const double le = shfl(E[je], src);
+        if (u0) { P0[0] = fma(-lp, lk0, P0[0]); E[0] = fma(-le, lk0, E[0]); }
+        if (u1) { P0[1] = fma(-lp, lk1, P0[1]); E[1] = fma(-le, lk1, E[1]); }
     }
     if (r < 2 * q) P0[0] = 0.0;
     if (r < 2 * q + 1) P0[1] = 0.0;
     U[JB][0] = E[0];
     U[JB][1] = E[1];
+    if constexpr (JB + 1 < NT) {
+        // W[r][2q+e] = U[2q+e][r], which lives in lane (2q+e, r/2), register r%2
+        const int s0 = 8 * q + (r >> 1), s1 = s0 + 4;
+        const double a0 = shfl(E[0], s0), b0 = shfl(E[1], s0);
+        const double a1 = shfl(E[0], s1), b1 = shfl(E[1], s1);
+        const double W0 = (r & 1) ? b0 : a0, W1 = (r & 1) ? b1 : a1;
+#pragma unroll
+        for (int I = JB + 1; I < NT; ++I) {
+            double c[2] = {0.0, 0.0};
+            mma_nt(c, A[tri(I, JB)][0], A[tri(I, JB)][1], W0, W1);
+            A[tri(I, JB)][0] = c[0];
+            A[tri(I, JB)][1] = c[1];
+        }
+    }
 }
 
 template <int NT, int JB>
@@ -292,7 +310,8 @@ __device__ __forceinline__ void chol_solve(const double (&A)[Lay<NT>::NTRI][2], 
 // H-pass tile ownership: rows of the lower triangle owned by tile-half 0 (the rest belongs to half 1)
 // ------------------------------------------------------------------------------------------
 __host__ __device__ constexpr unsigned rowmask0(int NT) {
-    return NT == 4 ? 0x9u : NT == 5 ? 0x14u : NT == 6 ? 0x30u : NT == 7 ? 0x61u : NT == 8 ? 0xC4u : 0u;
+    return NT == 4 ? 0x9u : NT == 5 ? 0x14u : NT == 6 ? 0x30u : NT == 7 ? 0x61u : NT == 8 ? 0xC4u : NT == 9 ? 0x190u :
+           NT == 10 ? 0x380u : 0u;
 }
 template <int NT, int TH>
 __host__ __device__ constexpr bool owns(int I) { return (((rowmask0(NT) >> I) & 1u) != 0u) == (TH == 0); }
@@ -347,12 +366,34 @@ struct Pipe {
         bulk_g2s(stage0 + st * Lay<NT>::STAGE_D, Vt + (size_t)t0 * NT * 64, bytes, full + st);
     }
     // all threads; the staging area may have been used as scratch (generic proxy) since the last pass
-    __device__ __forceinline__ void begin(unsigned g0) const {
+    __device__ __forceinline__ void begin(unsigned g0, int nprefetch) const {
         __syncthreads();
         if (tid == 0) {
             fence_proxy_async();
-            for (int c = 0; c < NSTAGE - 1 && c < nch; ++c) issue(c, g0 + c);
+            for (int c = 0; c < nprefetch && c < nch; ++c) issue(c, g0 + c);
         }
+    }
+    // pair variant: chunks c and c+1 are consumed together; thread 0 first issues chunks c+2 and c+3, whose
+    // stages were released by every warp in the previous pair iteration
+    __device__ __forceinline__ const double* wait2(int c, unsigned g0, const double*& second) const {
+        static_assert(NSTAGE == 4, "pair consumption assumes four stages");
+        if (tid == 0) {
+#pragma unroll
+            for (int d = 2; d < 4; ++d) {
+                const int cn = c + d;
+                if (cn < nch) {
+                    const unsigned gp = g0 + cn - NSTAGE;
+                    if (cn >= NSTAGE) mbar_wait(empty + gp % NSTAGE, (gp / NSTAGE) & 1);
+                    issue(cn, g0 + cn);
+                }
+            }
+        }
+        __syncwarp();
+        const unsigned g = g0 + c;
+        mbar_wait(full + g % NSTAGE, (g / NSTAGE) & 1);
+        if (c + 1 < nch) mbar_wait(full + (g + 1) % NSTAGE, ((g + 1) / NSTAGE) & 1);
+        second = stage0 + ((g + 1) % NSTAGE) * Lay<NT>::STAGE_D;
+        return stage0 + (g % NSTAGE) * Lay<NT>::STAGE_D;
     }
     // wait for chunk c of the pass; thread 0 first tops the pipeline up (the stage of chunk c-1 is refilled)
     __device__ __forceinline__ const double* wait(int c, unsigned g0) const {
@@ -482,7 +523,7 @@ __global__ void __launch_bounds__(NTHR, 2) sweep2_kernel(const SweepArgs a) {
     auto tpass = [&]() {
         const unsigned g0 = ctl.gchunk;
         const int nuniq = ctl.nuniq;
-        pipe.begin(g0);
+        pipe.begin(g0, 2);
         double tA[NT][2];
 #pragma unroll
         for (int jt = 0; jt < NT; ++jt) {
@@ -496,26 +537,38 @@ __global__ void __launch_bounds__(NTHR, 2) sweep2_kernel(const SweepArgs a) {
         const bool live = r < nuniq;
         double* const wrow = wscr + (size_t)(live ? ctl.urow[r] : 0) * rowlen;
         double* const hrow = hscr + (size_t)(live ? ctl.urow[r] : 0) * rowlen;
-        for (int c = 0; c < nch; ++c) {
-            const double* stage = pipe.wait(c, g0);
-            const int kt = c * CH + warp;
-            if (kt < n_kt) {
-                const double* tile0 = stage + warp * NT * 64;
-                double C0[2] = {0.0, 0.0}, C1[2] = {0.0, 0.0};
+        // two chunks (= two k-tiles of this warp) per iteration, interleaved so that the dependent chains of
+        // one tile (MMA accumulation, exp) overlap with the other's
+        for (int c = 0; c < nch; c += 2) {
+            const double* stB;
+            const double* stA = pipe.wait2(c, g0, stB);
+            const int ktA = c * CH + warp, ktB = ktA + CH;
+            const bool vA = ktA < n_kt, vB = ktB < n_kt;
+            const double* tile[2] = {stA + warp * NT * 64, vB ? stB + warp * NT * 64 : stA + warp * NT * 64};
+            double C[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
 #pragma unroll
-                for (int jt = 0; jt < NT; ++jt) {
-                    const double2 vv = *reinterpret_cast<const double2*>(tile0 + jt * 64 + offX);
-                    dmma(C0, tA[jt][0], vv.x);
-                    dmma(C1, tA[jt][1], vv.y);
+            for (int jt = 0; jt < NT; ++jt) {
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const double2 vv = *reinterpret_cast<const double2*>(tile[t] + jt * 64 + offX);
+                    dmma(C[t][0], tA[jt][0], vv.x);
+                    dmma(C[t][1], tA[jt][1], vv.y);
                 }
-                double Hv[2], Wv[2];
-                const int k0 = kt * 8 + 2 * q;
-                const double2 Dv = (k0 + 1 < a.n_omega) ? *reinterpret_cast<const double2*>(a.D + k0)
-                                                        : make_double2(k0 < a.n_omega ? a.D[k0] : 0.0, 0.0);
+            }
+            double Hv[2][2], Wv[2][2];
+            int k0[2] = {ktA * 8 + 2 * q, ktB * 8 + 2 * q};
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const bool valid = t ? vB : vA;
+                double2 Dv = make_double2(0.0, 0.0);
+                if (valid) {
+                    if (k0[t] + 1 < a.n_omega) Dv = *reinterpret_cast<const double2*>(a.D + k0[t]);
+                    else if (k0[t] < a.n_omega) Dv.x = a.D[k0[t]];
+                }
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     const double Dk = i ? Dv.y : Dv.x;
-                    const double x = C0[i] + C1[i];
+                    const double x = C[t][0][i] + C[t][1][i];
                     const double ex = exp(x);
                     double H, W, st_;
                     if (!pm) {
@@ -532,21 +585,26 @@ __global__ void __launch_bounds__(NTHR, 2) sweep2_kernel(const SweepArgs a) {
                         const double lm = (em <= 1e-100) ? -230.25850929940458 : -x;
                         st_ = (Hp - Dk - Hp * lp) + (Hm - Dk - Hm * lm);
                     }
-                    if (Dk == 0.0) { H = 0.0; W = 0.0; st_ = 0.0; }   // padded rows
+                    if (Dk == 0.0) { H = 0.0; W = 0.0; st_ = 0.0; }   // padded rows / missing tile
                     sacc += st_;
-                    Hv[i] = H; Wv[i] = W;
+                    Hv[t][i] = H; Wv[t][i] = W;
                 }
-                if (live) {
-                    *reinterpret_cast<double2*>(wrow + k0) = make_double2(Wv[0], Wv[1]);
-                    if (pm) *reinterpret_cast<double2*>(hrow + k0) = make_double2(Hv[0], Hv[1]);
+                if (live && valid) {
+                    *reinterpret_cast<double2*>(wrow + k0[t]) = make_double2(Wv[t][0], Wv[t][1]);
+                    if (pm) *reinterpret_cast<double2*>(hrow + k0[t]) = make_double2(Hv[t][0], Hv[t][1]);
                 }
+            }
 #pragma unroll
-                for (int jt = 0; jt < NT; ++jt) {
-                    dmma(yacc[jt], Hv[0], tile0[jt * 64 + offY0]);
-                    dmma(yacc[jt], Hv[1], tile0[jt * 64 + offY1]);
+            for (int t = 0; t < 2; ++t) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int off = e ? offY1 : offY0;
+#pragma unroll
+                    for (int jt = 0; jt < NT; ++jt) dmma(yacc[jt], Hv[t][e], tile[t][jt * 64 + off]);
                 }
             }
             pipe.release(c, g0);
+            if (c + 1 < nch) pipe.release(c + 1, g0);
         }
         __syncthreads();                                   // staging area is free: reuse as yred[4][8][SP]
         if (tid == 0) ctl.gchunk = g0 + nch;
@@ -584,7 +642,7 @@ __global__ void __launch_bounds__(NTHR, 2) sweep2_kernel(const SweepArgs a) {
     // ---- H-pass: Z = V'^T diag(w) V' with w from scratch row `row` -> Zfull (all NT x NT tiles, C layout) ----
     auto hpass = [&](int row) {
         const unsigned g0 = ctl.gchunk;
-        pipe.begin(g0);
+        pipe.begin(g0, NSTAGE - 1);
         const int kg = warp >> 1, th = warp & 1;
         const double* wrow = wscr + (size_t)row * rowlen;
         double* Zf = sm + LY::o_stage;
@@ -830,89 +888,97 @@ __global__ void __launch_bounds__(NTHR, 2) sweep2_kernel(const SweepArgs a) {
             __syncthreads();
             for (;;) {
                 if (warp == 0) {
-                    int done = 0;
-                    if (lane == 0) {
-                        LM& L = ctl.lm;
-                        auto look_real = [&](double mu, int, double, double& Q, int& id) -> bool {
-                            for (int i = 0; i < ctl.nb; ++i)
-                                if (ctl.bmu[i] == mu) {
-                                    id = ctl.bslot[i]; Q = ctl.uQ[id];
-                                    ctl.ns++; if (!ctl.ufail[id]) ctl.nq++;
-                                    return true;
-                                }
-                            return false;
-                        };
-                        done = lm_run(L, a.nu, a.max_mu, eps_nu, look_real) ? 1 : 0;
-                        if (!done) {
-                            // carry the live candidate of the old batch (its dv, y, chi2, S and scratch row)
-                            int live = (L.phase == PH_WALK) ? L.dvnew : (L.phase == PH_PROBE ? L.dv : ID_NONE);
-                            if (live >= 0 && live < MAXB) {
-                                ctl.action = live;               // vectors are copied by the whole warp below
-                                ctl.uQ[ID_CARRY] = ctl.uQ[live]; ctl.uchi2[ID_CARRY] = ctl.uchi2[live]; ctl.uS[ID_CARRY] = ctl.uS[live];
-                                ctl.ufail[ID_CARRY] = ctl.ufail[live]; ctl.urow[ID_CARRY] = ctl.urow[live];
-                                if (L.phase == PH_WALK) L.dvnew = ID_CARRY; else L.dv = ID_CARRY;
-                            } else {
-                                ctl.action = -1;
-                                if (live == ID_NONE) ctl.urow[ID_CARRY] = -1;
-                            }
-                            // plan: continue a copy of the machine with pretended outcomes to list the next dampings
-                            LM P = L;
-                            int nn = 0;
-                            double nmu[MAXB], nq_[MAXB];
-                            const bool dir_up = ctl.dir_up != 0;
-                            auto look_plan = [&](double mu, int kind, double Qref, double& Q, int& id) -> bool {
-                                for (int i = 0; i < nn; ++i) if (nmu[i] == mu) { Q = nq_[i]; id = 100 + i; return true; }
-                                if (nn == MAXB) return false;
-                                double pq;
-                                if (kind == 0) pq = isnan(Qref) ? 0.0 : Qref;
-                                else if (kind == 1) pq = dir_up ? Qref - (1.0 + fabs(Qref)) : Qref;
-                                else pq = Qref - (1.0 + fabs(Qref));
-                                nmu[nn] = mu; nq_[nn] = pq; id = 100 + nn; Q = pq; ++nn;
-                                return true;
-                            };
-                            lm_run(P, a.nu, a.max_mu, eps_nu, look_plan);
-                            ctl.nb = nn;
-                            for (int i = 0; i < nn; ++i) ctl.bmu[i] = nmu[i];
+                    // The whole warp runs the (scalar, warp-uniform) state machine so that table searches and the
+                    // "same shifted diagonal" tests are ballots instead of serial loops.
+                    LM L = ctl.lm;
+                    int ns = ctl.ns, nq = ctl.nq;
+                    const double* jdv = sm + LY::o_jd;
+                    // two dampings are equivalent when they give bitwise the same matrix J + shift(mu)
+                    double jdmin = INFINITY;
+                    for (int k = lane; k < s; k += 32) jdmin = fmin(jdmin, fabs(jdv[k]));
+                    jdmin = -warp_max(-jdmin);
+                    auto equiv = [&](double ma, double mb) -> bool {
+                        if (ma == mb) return true;
+                        // the entry with the smallest |J_kk| can only round to the same value if the dampings
+                        // differ by less than two of its ulps: cheap exit for everything but vanishing dampings
+                        if (!bryan && fabs(ma - mb) > 4.5e-16 * (jdmin + fmax(ma, mb))) return false;
+                        bool same = true;
+                        for (int k = lane; k < s; k += 32) {
+                            const double jd = jdv[k];
+                            same = same && ((jd + shift_of(k, ma)) == (jd + shift_of(k, mb)));
                         }
-                        ctl.conv = done;
-                    }
-                    __syncwarp();
-                    done = ctl.conv;
+                        return __all_sync(0xffffffffu, same);
+                    };
+                    const int nb0 = ctl.nb, nu0 = ctl.nuniq;
+                    auto look_real = [&](double mu, int, double, double& Q, int& id) -> bool {
+                        const unsigned m = __ballot_sync(0xffffffffu, lane < nb0 && ctl.bmu[lane] == mu);
+                        id = -1;
+                        if (m) id = ctl.bslot[__ffs(m) - 1];
+                        else {
+                            for (int u = 0; u < nu0 && id < 0; ++u) if (equiv(mu, ctl.umu[u])) id = u;
+                            if (id < 0 && ctl.urow[ID_CARRY] >= 0 && equiv(mu, ctl.umu[ID_CARRY])) id = ID_CARRY;
+                        }
+                        if (id < 0) return false;
+                        Q = ctl.uQ[id];
+                        ++ns; if (!ctl.ufail[id]) ++nq;
+                        return true;
+                    };
+                    const int done = lm_run(L, a.nu, a.max_mu, eps_nu, look_real) ? 1 : 0;
                     if (!done) {
-                        const int live = ctl.action;
-                        if (live >= 0) {
+                        // carry the live candidate of the old batch (its dv, y, chi2, S, damping and scratch row)
+                        const int live = (L.phase == PH_WALK) ? L.dvnew : (L.phase == PH_PROBE ? L.dv : ID_NONE);
+                        if (live >= 0 && live < MAXB) {
                             for (int i = lane; i < SP; i += 32) {
                                 sm[LY::o_cdv + i] = sm[LY::o_dvb + live * SP + i];
                                 sm[LY::o_cy + i] = sm[LY::o_yb + live * SP + i];
                             }
+                            if (lane == 0) {
+                                ctl.uQ[ID_CARRY] = ctl.uQ[live]; ctl.uchi2[ID_CARRY] = ctl.uchi2[live]; ctl.uS[ID_CARRY] = ctl.uS[live];
+                                ctl.ufail[ID_CARRY] = ctl.ufail[live]; ctl.urow[ID_CARRY] = ctl.urow[live];
+                                ctl.umu[ID_CARRY] = ctl.umu[live];
+                            }
+                            if (L.phase == PH_WALK) L.dvnew = ID_CARRY; else L.dv = ID_CARRY;
+                        } else if (live == ID_NONE) {
+                            if (lane == 0) ctl.urow[ID_CARRY] = -1;
                         }
-                        // dedup: two dampings whose shifted diagonals are bitwise identical give identical trials
-                        const int nb = ctl.nb;
-                        int nuniq = 0;
-                        int rowp = 0;
-                        for (int i = 0; i < nb; ++i) {
-                            const double mu_i = ctl.bmu[i];
-                            int alias = -1;
-                            for (int u = 0; u < nuniq && alias < 0; ++u) {
-                                const double mu_u = ctl.umu[u];
-                                bool same = true;
-                                for (int k = lane; k < s; k += 32) {
-                                    const double jd = sm[LY::o_jd + k];
-                                    same = same && ((jd + shift_of(k, mu_i)) == (jd + shift_of(k, mu_u)));
+                        __syncwarp();
+                        // plan: continue a copy of the machine with pretended outcomes to list the next dampings
+                        LM P = L;
+                        int np = 0, npu = 0;
+                        const bool dir_up = ctl.dir_up != 0;
+                        const bool have_carry = ctl.urow[ID_CARRY] >= 0;
+                        const double cmu = ctl.umu[ID_CARRY];
+                        auto look_plan = [&](double mu, int kind, double Qref, double& Q, int& id) -> bool {
+                            if (have_carry && equiv(mu, cmu)) { Q = ctl.uQ[ID_CARRY]; id = ID_CARRY; return true; }
+                            const unsigned m = __ballot_sync(0xffffffffu, lane < np && ctl.bmu[lane] == mu);
+                            if (m) { const int u = ctl.bslot[__ffs(m) - 1]; Q = ctl.pq[u]; id = 100 + u; return true; }
+                            for (int u = 0; u < npu; ++u)
+                                if (equiv(mu, ctl.umu[u])) {
+                                    if (np < NTAB) { if (lane == 0) { ctl.bmu[np] = mu; ctl.bslot[np] = u; } ++np; __syncwarp(); }
+                                    Q = ctl.pq[u]; id = 100 + u;
+                                    return true;
                                 }
-                                if (__all_sync(0xffffffffu, same)) alias = u;
-                            }
-                            if (alias < 0) {
-                                alias = nuniq++;
-                                if (rowp == ctl.urow[ID_CARRY]) ++rowp;
-                                if (lane == 0) { ctl.umu[alias] = mu_i; ctl.urow[alias] = rowp; ctl.ufail[alias] = 0; }
-                                ++rowp;
-                            }
-                            if (lane == 0) ctl.bslot[i] = alias;
+                            if (npu == MAXB || np == NTAB) return false;
+                            double pv;
+                            if (kind == 0) pv = isnan(Qref) ? 0.0 : Qref;                        // first trial / pump: "accepted"
+                            else if (kind == 1) pv = dir_up ? Qref - (1.0 + fabs(Qref)) : Qref + (1.0 + fabs(Qref));
+                            else pv = Qref - (1.0 + fabs(Qref));                                  // walk: "still improving"
+                            if (lane == 0) { ctl.bmu[np] = mu; ctl.bslot[np] = npu; ctl.umu[npu] = mu; ctl.pq[npu] = pv; }
+                            id = 100 + npu; Q = pv; ++np; ++npu;
                             __syncwarp();
+                            return true;
+                        };
+                        lm_run(P, a.nu, a.max_mu, eps_nu, look_plan);
+                        if (lane == 0) {
+                            ctl.nb = np; ctl.nuniq = npu;
+                            int rowp = 0;
+                            for (int u = 0; u < npu; ++u) {
+                                if (rowp == ctl.urow[ID_CARRY]) ++rowp;
+                                ctl.urow[u] = rowp++; ctl.ufail[u] = 0;
+                            }
                         }
-                        if (lane == 0) ctl.nuniq = nuniq;
                     }
+                    if (lane == 0) { ctl.lm = L; ctl.ns = ns; ctl.nq = nq; ctl.conv = done; }
                 }
                 __syncthreads();
                 if (ctl.conv) break;

@@ -50,7 +50,7 @@ class SharedProblem(object):
     this rotation because mu*1 is."""
 
     def __init__(self, K, err, D, delta, variant="normal", reduce_singular_space=1.e-14, device=None,
-                 svd="jacobi", A_init=None, max_nsv=None, engine=0):
+                 svd="jacobi", A_init=None, max_nsv=None, engine=0, rank_floor=1.e-14):
         torch = _torch()
         if not torch.cuda.is_available():
             raise _lib.MaxEntLibraryError("maxent_b200 needs a CUDA device (no CPU fallback)")
@@ -66,8 +66,15 @@ class SharedProblem(object):
             self.variant = variant
             # ---- SVD of the kernel (KernelSVD.svd, python/kernels.py:53-64) ----
             U, S, V = self._svd(K, svd)
-            thr = reduce_singular_space
-            keep = torch.nonzero(S >= (thr if thr is not None else -1.0)).flatten()
+            # reduce_singular_space is an ABSOLUTE threshold (python/kernels.py:101-122).  Below
+            # rank_floor * S[0] the computed singular triplets are rounding noise (which of them pass an absolute
+            # 1e-14 depends on the SVD implementation, and their left vectors are not orthonormal any more), so the
+            # cut is honoured only down to the numerical rank -- the one documented deviation; the
+            # optimum A_alpha does not depend on those directions (last item).
+            thr = -1.0 if reduce_singular_space is None else float(reduce_singular_space)
+            self.n_sv_requested = int((S >= thr).sum())
+            thr = max(thr, float(rank_floor) * float(S[0]))
+            keep = torch.nonzero(S >= thr).flatten()
             cap = _lib.MX_MAX_NSV if max_nsv is None else max_nsv
             self.n_sv_uncapped = int(keep.numel())
             if keep.numel() > cap:

@@ -70,6 +70,23 @@ def panel(tiles, E):
     return ok, logdet
 
 
+def panel_w(tiles, E):
+    """The variant used by mx_sweep2.cuh: column steps on the diagonal tile and the identity tile only, then
+    L[I][JB] = A[I][JB] W^T through two MMAs per tile with W = U^T (in-register transpose)."""
+    P0 = tiles[0]
+    ok, logdet = panel([P0], E)
+    s0 = 8 * Qn + (R >> 1)
+    s1 = s0 + 4
+    a0, b0 = shfl(E[0], s0), shfl(E[1], s0)
+    a1, b1 = shfl(E[0], s1), shfl(E[1], s1)
+    W0 = np.where(R & 1, b0, a0)
+    W1 = np.where(R & 1, b1, a1)
+    for T in tiles[1:]:
+        c = mma_nt((np.zeros(32), np.zeros(32)), (T[0], T[1]), (W0, W1))
+        T[0], T[1] = c[0], c[1]
+    return ok, logdet
+
+
 def cholesky(A, NT):
     """A: dict (I,J)->[t0,t1] lower tiles.  In place -> L; returns (ok, logdet, U list)."""
     U = []
@@ -78,7 +95,7 @@ def cholesky(A, NT):
     for jb in range(NT):
         E = list(from_tile(np.eye(8)))
         col = [A[(I, jb)] for I in range(jb, NT)]
-        o, ld = panel(col, E)
+        o, ld = panel_w(col, E)
         ok &= o
         logdet += ld
         U.append(E)
