@@ -1,12 +1,13 @@
 // Fused MaxEnt alpha sweep for sm_100a (B200), second generation ("spectrum per CTA").
 //
-// One 4-warp CTA owns one spectrum at a time (persistent CTAs, atomic work counter, 2 CTAs per SM) and
-// runs the whole alpha mesh for it.  The Levenberg-Marquardt iteration of the reference
+// One 8-warp CTA owns one spectrum at a time (persistent CTAs, atomic work counter, 2 CTAs per SM at 128
+// registers per thread; the four solver warps borrow the other warp group's registers with setmaxnreg
+// while they hold a whole matrix in registers) and runs the whole alpha mesh for it.  The Levenberg-Marquardt iteration of the reference
 // (levenberg_minimizer.py:123-248) asks for Q(v - dv(mu)) at a chain of damping values
 // mu, 1.3 mu, 1.3^2 mu ... that is decided by comparisons of the Q values.  Instead of evaluating the
 // chain one trial at a time (latency bound), the CTA *speculates*: it plans the next up-to-8 damping
-// values the reference would visit, factorises the 8 shifted Hessians concurrently (one warp per
-// matrix, register-resident DMMA-blocked Cholesky) and evaluates the 8 trial vectors in ONE pass over
+// values the reference would visit, factorises the 8 shifted Hessians (one warp per matrix, four at a
+// time, register-resident DMMA-blocked Cholesky) and evaluates the 8 trial vectors in ONE pass over
 // V' where the 8 trials are the M dimension of the FP64 tensor-core MMA (m8n8k4):
 //     T-pass:  x = V' t_b ; H = D exp(x) ; y_b = V'^T H ; S_b ; w_b -> scratch      (8 trials)
 //     H-pass:  Z = V'^T diag(w) V'                                                   (accepted point)
@@ -33,8 +34,10 @@ using mx::SweepArgs;
 using mx::dmma;
 using mx::tile_off;
 
-constexpr int NWARP = 4;
+constexpr int NWARP = 8;        // two warp groups: group 0 also runs the register-hungry Cholesky phase
+constexpr int NSOLVE = 4;       // warps that factorise (one warp group, see regs_to_solvers)
 constexpr int NTHR = NWARP * 32;
+constexpr int REG_HI = 216, REG_LO = 40, REG_EVEN = 128;   // setmaxnreg budgets: 128 * (216 + 40) = 256 * 128
 constexpr int CH = 4;          // k-tiles (8 omega rows each) per staged chunk = one per warp in the T-pass
 constexpr int NSTAGE = 4;
 constexpr int MAXB = 8;        // unique trials per batch = M of the MMA
@@ -112,7 +115,7 @@ struct Lay {
     static constexpr int SP = 8 * NT;
     static constexpr int NTRI = NT * (NT + 1) / 2;
     static constexpr int STAGE_D = CH * NT * 64;
-    static constexpr int o_stage = 0;                              // NSTAGE x STAGE_D ; aliases: Zfull [NT*NT*64], yred [4][8][SP]
+    static constexpr int o_stage = 0;                              // NSTAGE x STAGE_D ; aliases: Zfull [NT*NT*64], yred [NWARP][8][SP]
     static constexpr int o_J = o_stage + NSTAGE * STAGE_D;         // NTRI tiles, C layout
     static constexpr int o_tb = o_J + NTRI * 64;                   // [8][SP] trial vectors t_b = v - dv_b
     static constexpr int o_dvb = o_tb + MAXB * SP;                 // [8][SP]
@@ -128,8 +131,8 @@ struct Lay {
     static constexpr int o_lam = o_xi + SP;
     static constexpr int o_ycur = o_lam + SP;
     static constexpr int o_jd = o_ycur + SP;                       // diagonal of J
-    static constexpr int o_sred = o_jd + SP;                       // [4][8] entropy partials
-    static constexpr int o_ctl = o_sred + 32;                      // Ctl block (192 doubles reserved)
+    static constexpr int o_sred = o_jd + SP;                       // [NWARP][8] entropy partials
+    static constexpr int o_ctl = o_sred + NWARP * 8;                      // Ctl block (192 doubles reserved)
     static constexpr int o_bar = o_ctl + 192;                      // 2*NSTAGE mbarriers
     static constexpr int total = o_bar + 2 * NSTAGE;
     static_assert(NT * NT * 64 <= NSTAGE * STAGE_D, "Zfull must fit in the staging area");
@@ -277,21 +280,27 @@ __device__ __forceinline__ void chol_steps(double (&A)[Lay<NT>::NTRI][2], double
 }
 
 // Solve L L^T x = rhs with the factor in registers.  rhs: shared vector (8 NT); x is returned
-// row-replicated: xr[I] = x[8 I + r] on every lane of row r.
+// row-replicated: xr[I] = x[8 I + r] on every lane of row r.  The intermediate z = L^{-1} rhs is parked in
+// `zscr` (8 NT doubles of shared memory owned by this warp) to keep the register footprint down.
 template <int NT>
 __device__ __forceinline__ void chol_solve(const double (&A)[Lay<NT>::NTRI][2], const double (&U)[NT][2],
-                                           const double* __restrict__ rhs, double (&xr)[NT], int r) {
-    double zc[NT][2];
+                                           const double* __restrict__ rhs, double (&xr)[NT], int r, int q,
+                                           double* __restrict__ zscr) {
+    {
+        double zc[NT][2];
 #pragma unroll
-    for (int jb = 0; jb < NT; ++jb) {
-        double acc = 0.0;
+        for (int jb = 0; jb < NT; ++jb) {
+            double acc = 0.0;
 #pragma unroll
-        for (int J = 0; J < jb; ++J) acc = fma(A[tri(jb, J)][0], zc[J][0], fma(A[tri(jb, J)][1], zc[J][1], acc));
-        double rr = rhs[8 * jb + r];
-        if (jb > 0) rr -= quadreduce(acc);
-        zc[jb][0] = colreduce(U[jb][0] * rr);
-        zc[jb][1] = colreduce(U[jb][1] * rr);
+            for (int J = 0; J < jb; ++J) acc = fma(A[tri(jb, J)][0], zc[J][0], fma(A[tri(jb, J)][1], zc[J][1], acc));
+            double rr = rhs[8 * jb + r];
+            if (jb > 0) rr -= quadreduce(acc);
+            zc[jb][0] = colreduce(U[jb][0] * rr);
+            zc[jb][1] = colreduce(U[jb][1] * rr);
+            if (r == 0) *reinterpret_cast<double2*>(zscr + 8 * jb + 2 * q) = make_double2(zc[jb][0], zc[jb][1]);
+        }
     }
+    __syncwarp();
 #pragma unroll
     for (int jb = NT - 1; jb >= 0; --jb) {
         double c0 = 0.0, c1 = 0.0;
@@ -300,10 +309,12 @@ __device__ __forceinline__ void chol_solve(const double (&A)[Lay<NT>::NTRI][2], 
             c0 = fma(A[tri(I, jb)][0], xr[I], c0);
             c1 = fma(A[tri(I, jb)][1], xr[I], c1);
         }
-        double z0 = zc[jb][0], z1 = zc[jb][1];
+        const double2 z = *reinterpret_cast<const double2*>(zscr + 8 * jb + 2 * q);
+        double z0 = z.x, z1 = z.y;
         if (jb < NT - 1) { z0 -= colreduce(c0); z1 -= colreduce(c1); }
         xr[jb] = quadreduce(fma(U[jb][0], z0, U[jb][1] * z1));
     }
+    __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -430,58 +441,55 @@ __device__ __forceinline__ void hpass_body(const Pipe<NT>& pipe, unsigned g0, co
 #pragma unroll
             for (int J = 0; J <= I; ++J) { zacc[tri(I, J)][0] = 0.0; zacc[tri(I, J)][1] = 0.0; }
         }
-    // this warp handles k-tiles (c*CH + kg) and (c*CH + kg + 2) of every chunk; w is prefetched one chunk ahead
+    // this warp handles k-tile (c*CH + kg) of every chunk; w is prefetched two chunks ahead
+    static_assert(CH == NWARP / 2, "one k-tile of every chunk per k-group");
     auto loadw = [&](int kt) -> double2 {
         if (kt < n_kt) return *reinterpret_cast<const double2*>(wrow + kt * 8 + 2 * q);
         return make_double2(0.0, 0.0);
     };
-    double2 wa = loadw(kg), wb = loadw(kg + 2);
+    double2 w0 = loadw(kg), w1 = loadw(CH + kg);
     for (int c = 0; c < nch; ++c) {
         const double* stage = pipe.wait(c, g0);
-        const double2 wa_n = loadw((c + 1) * CH + kg), wb_n = loadw((c + 1) * CH + kg + 2);
-        const int kt0 = c * CH + kg, kt1 = kt0 + 2;
-        if (kt0 < n_kt) hpass_ktile<NT, TH>(stage + kg * NT * 64, wa.x, wa.y, offY0, offY1, zacc);
-        if (kt1 < n_kt) hpass_ktile<NT, TH>(stage + (kg + 2) * NT * 64, wb.x, wb.y, offY0, offY1, zacc);
-        wa = wa_n; wb = wb_n;
+        const double2 w2 = loadw((c + 2) * CH + kg);
+        const int kt = c * CH + kg;
+        if (kt < n_kt) hpass_ktile<NT, TH>(stage + kg * NT * 64, w0.x, w0.y, offY0, offY1, zacc);
+        w0 = w1; w1 = w2;
         pipe.release(c, g0);
     }
     __syncthreads();                                       // every warp is done with the staging area
-    if (kg == 0) {
+    // the k-groups add their partial tiles in a fixed order (deterministic sums); the last one mirrors
+#pragma unroll 1
+    for (int g = 0; g < CH; ++g) {
+        if (kg == g) {
 #pragma unroll
-        for (int I = 0; I < NT; ++I)
-            if (owns<NT, TH>(I)) {
+            for (int I = 0; I < NT; ++I)
+                if (owns<NT, TH>(I)) {
 #pragma unroll
-                for (int J = 0; J <= I; ++J)
-                    *reinterpret_cast<double2*>(Zf + (I * NT + J) * 64 + 2 * lane) = make_double2(zacc[tri(I, J)][0], zacc[tri(I, J)][1]);
-            }
-    }
-    __syncthreads();
-    if (kg == 1) {
-#pragma unroll
-        for (int I = 0; I < NT; ++I)
-            if (owns<NT, TH>(I)) {
-#pragma unroll
-                for (int J = 0; J <= I; ++J) {
-                    double2* p = reinterpret_cast<double2*>(Zf + (I * NT + J) * 64 + 2 * lane);
-                    const double2 o = *p;
-                    const double2 vv = make_double2(o.x + zacc[tri(I, J)][0], o.y + zacc[tri(I, J)][1]);
-                    *p = vv;
-                    if (I != J) {                          // mirror: tile (J, I) = transpose
-                        Zf[(J * NT + I) * 64 + (2 * q) * 8 + r] = vv.x;
-                        Zf[(J * NT + I) * 64 + (2 * q + 1) * 8 + r] = vv.y;
+                    for (int J = 0; J <= I; ++J) {
+                        double2* p = reinterpret_cast<double2*>(Zf + (I * NT + J) * 64 + 2 * lane);
+                        double2 vv = make_double2(zacc[tri(I, J)][0], zacc[tri(I, J)][1]);
+                        if (g > 0) { const double2 o = *p; vv.x += o.x; vv.y += o.y; }
+                        *p = vv;
+                        if (g == CH - 1 && I != J) {       // mirror: tile (J, I) = transpose
+                            Zf[(J * NT + I) * 64 + (2 * q) * 8 + r] = vv.x;
+                            Zf[(J * NT + I) * 64 + (2 * q + 1) * 8 + r] = vv.y;
+                        }
                     }
                 }
-            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
 template <int NT>
-__global__ void __launch_bounds__(NTHR, 2) sweep2_kernel(const SweepArgs a) {
+__global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const SweepArgs a) {
     using LY = Lay<NT>;
+    // NT <= 8: two CTAs per SM at 128 registers per thread, the solver warp group is lent registers for the
+    // Cholesky phase; NT > 8: one CTA per SM (shared memory), every thread owns 255 registers all the time
+    constexpr bool REGSPLIT = NT <= 8;
     constexpr int SP = LY::SP;
     constexpr int NTRI = LY::NTRI;
     extern __shared__ __align__(128) double sm[];
@@ -518,6 +526,23 @@ __global__ void __launch_bounds__(NTHR, 2) sweep2_kernel(const SweepArgs a) {
 
     const Pipe<NT> pipe{sm + LY::o_stage, a.Vt, bar_full, bar_empty, tid, lane, n_kt, nch};
 
+    // Register hand-over around a solver phase.  Every thread calls both; between them only warps < NSOLVE work,
+    // the others go straight to the closing barrier.
+    auto regs_to_solvers = [&]() {
+        if constexpr (REGSPLIT) {
+            if (warp < NSOLVE) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(REG_HI));
+            else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(REG_LO));
+        }
+    };
+    auto regs_back = [&]() {                              // ends with a CTA barrier
+        if constexpr (REGSPLIT) {
+            if (warp < NSOLVE) { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(REG_EVEN)); __syncthreads(); }
+            else { __syncthreads(); asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(REG_EVEN)); }
+        } else {
+            __syncthreads();
+        }
+    };
+
     // ---- T-pass: evaluate the cost function at the trial vectors tb[0..7] ---------------------------
     // Per unique trial u < nuniq: yb[u], uchi2, uS, uQ, and w (and H) rows in scratch.
     auto tpass = [&]() {
@@ -537,76 +562,66 @@ __global__ void __launch_bounds__(NTHR, 2) sweep2_kernel(const SweepArgs a) {
         const bool live = r < nuniq;
         double* const wrow = wscr + (size_t)(live ? ctl.urow[r] : 0) * rowlen;
         double* const hrow = hscr + (size_t)(live ? ctl.urow[r] : 0) * rowlen;
-        // two chunks (= two k-tiles of this warp) per iteration, interleaved so that the dependent chains of
-        // one tile (MMA accumulation, exp) overlap with the other's
+        // two chunks per iteration: warps 0-3 take the four k-tiles of chunk c, warps 4-7 those of chunk c+1
+        const int half = warp >> 2, wq = warp & 3;
         for (int c = 0; c < nch; c += 2) {
             const double* stB;
             const double* stA = pipe.wait2(c, g0, stB);
-            const int ktA = c * CH + warp, ktB = ktA + CH;
-            const bool vA = ktA < n_kt, vB = ktB < n_kt;
-            const double* tile[2] = {stA + warp * NT * 64, vB ? stB + warp * NT * 64 : stA + warp * NT * 64};
-            double C[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+            const int kt = (c + half) * CH + wq;
+            const bool valid = kt < n_kt;
+            const double* tile = ((half && valid) ? stB : stA) + wq * NT * 64;
+            double C0[2] = {0.0, 0.0}, C1[2] = {0.0, 0.0};
 #pragma unroll
             for (int jt = 0; jt < NT; ++jt) {
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    const double2 vv = *reinterpret_cast<const double2*>(tile[t] + jt * 64 + offX);
-                    dmma(C[t][0], tA[jt][0], vv.x);
-                    dmma(C[t][1], tA[jt][1], vv.y);
-                }
+                const double2 vv = *reinterpret_cast<const double2*>(tile + jt * 64 + offX);
+                dmma(C0, tA[jt][0], vv.x);
+                dmma(C1, tA[jt][1], vv.y);
             }
-            double Hv[2][2], Wv[2][2];
-            int k0[2] = {ktA * 8 + 2 * q, ktB * 8 + 2 * q};
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                const bool valid = t ? vB : vA;
-                double2 Dv = make_double2(0.0, 0.0);
-                if (valid) {
-                    if (k0[t] + 1 < a.n_omega) Dv = *reinterpret_cast<const double2*>(a.D + k0[t]);
-                    else if (k0[t] < a.n_omega) Dv.x = a.D[k0[t]];
-                }
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const double Dk = i ? Dv.y : Dv.x;
-                    const double x = C[t][0][i] + C[t][1][i];
-                    const double ex = exp(x);
-                    double H, W, st_;
-                    if (!pm) {
-                        // H = D e^x ; S += H - D - H log(H/D), safelog clamp at 1e-100  (functions.py:53-56,508-510)
-                        H = Dk * ex; W = H;
-                        const double lg = (ex <= 1e-100) ? -230.25850929940458 : x;
-                        st_ = H - Dk - H * lg;
-                    } else {
-                        // H = D (e^x - e^-x) ; w = D (e^x + e^-x) ; S = S_n(H+) + S_n(H-)   (functions.py:544-564,778-786)
-                        const double em = exp(-x);
-                        const double Hp = Dk * ex, Hm = Dk * em;
-                        H = Hp - Hm; W = Hp + Hm;
-                        const double lp = (ex <= 1e-100) ? -230.25850929940458 : x;
-                        const double lm = (em <= 1e-100) ? -230.25850929940458 : -x;
-                        st_ = (Hp - Dk - Hp * lp) + (Hm - Dk - Hm * lm);
-                    }
-                    if (Dk == 0.0) { H = 0.0; W = 0.0; st_ = 0.0; }   // padded rows / missing tile
-                    sacc += st_;
-                    Hv[t][i] = H; Wv[t][i] = W;
-                }
-                if (live && valid) {
-                    *reinterpret_cast<double2*>(wrow + k0[t]) = make_double2(Wv[t][0], Wv[t][1]);
-                    if (pm) *reinterpret_cast<double2*>(hrow + k0[t]) = make_double2(Hv[t][0], Hv[t][1]);
-                }
+            double Hv[2], Wv[2];
+            const int k0 = kt * 8 + 2 * q;
+            double2 Dv = make_double2(0.0, 0.0);
+            if (valid) {
+                if (k0 + 1 < a.n_omega) Dv = *reinterpret_cast<const double2*>(a.D + k0);
+                else if (k0 < a.n_omega) Dv.x = a.D[k0];
             }
 #pragma unroll
-            for (int t = 0; t < 2; ++t) {
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int off = e ? offY1 : offY0;
-#pragma unroll
-                    for (int jt = 0; jt < NT; ++jt) dmma(yacc[jt], Hv[t][e], tile[t][jt * 64 + off]);
+            for (int i = 0; i < 2; ++i) {
+                const double Dk = i ? Dv.y : Dv.x;
+                const double x = C0[i] + C1[i];
+                const double ex = exp(x);
+                double H, W, st_;
+                if (!pm) {
+                    // H = D e^x ; S += H - D - H log(H/D), safelog clamp at 1e-100  (functions.py:53-56,508-510)
+                    H = Dk * ex; W = H;
+                    const double lg = (ex <= 1e-100) ? -230.25850929940458 : x;
+                    st_ = H - Dk - H * lg;
+                } else {
+                    // H = D (e^x - e^-x) ; w = D (e^x + e^-x) ; S = S_n(H+) + S_n(H-)   (functions.py:544-564,778-786)
+                    const double em = exp(-x);
+                    const double Hp = Dk * ex, Hm = Dk * em;
+                    H = Hp - Hm; W = Hp + Hm;
+                    const double lp = (ex <= 1e-100) ? -230.25850929940458 : x;
+                    const double lm = (em <= 1e-100) ? -230.25850929940458 : -x;
+                    st_ = (Hp - Dk - Hp * lp) + (Hm - Dk - Hm * lm);
                 }
+                if (Dk == 0.0) { H = 0.0; W = 0.0; st_ = 0.0; }   // padded rows / missing tile
+                sacc += st_;
+                Hv[i] = H; Wv[i] = W;
+            }
+            if (live && valid) {
+                *reinterpret_cast<double2*>(wrow + k0) = make_double2(Wv[0], Wv[1]);
+                if (pm) *reinterpret_cast<double2*>(hrow + k0) = make_double2(Hv[0], Hv[1]);
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int off = e ? offY1 : offY0;
+#pragma unroll
+                for (int jt = 0; jt < NT; ++jt) dmma(yacc[jt], Hv[e], tile[jt * 64 + off]);
             }
             pipe.release(c, g0);
             if (c + 1 < nch) pipe.release(c + 1, g0);
         }
-        __syncthreads();                                   // staging area is free: reuse as yred[4][8][SP]
+        __syncthreads();                                   // staging area is free: reuse as yred[NWARP][8][SP]
         if (tid == 0) ctl.gchunk = g0 + nch;
         double* yred = sm + LY::o_stage;
 #pragma unroll
@@ -617,10 +632,12 @@ __global__ void __launch_bounds__(NTHR, 2) sweep2_kernel(const SweepArgs a) {
             if (q == 0) sm[LY::o_sred + warp * 8 + r] = sq;
         }
         __syncthreads();
+        static_assert(NWARP == 8, "fixed-order reduction tree over eight warps");
         for (int i = tid; i < MAXB * SP; i += NTHR) {
             const int b = i / SP, j = i - b * SP;
-            sm[LY::o_yb + i] = (yred[(0 * 8 + b) * SP + j] + yred[(1 * 8 + b) * SP + j]) +
-                               (yred[(2 * 8 + b) * SP + j] + yred[(3 * 8 + b) * SP + j]);
+            const double* y0 = yred + b * SP + j;
+            sm[LY::o_yb + i] = ((y0[0 * 8 * SP] + y0[1 * 8 * SP]) + (y0[2 * 8 * SP] + y0[3 * 8 * SP])) +
+                               ((y0[4 * 8 * SP] + y0[5 * 8 * SP]) + (y0[6 * 8 * SP] + y0[7 * 8 * SP]));
         }
         __syncthreads();
         for (int u = warp; u < nuniq; u += NWARP) {        // chi2 = |Xi y - g~|^2 + c0  (functions.py:358-360 in singular space)
@@ -630,7 +647,8 @@ __global__ void __launch_bounds__(NTHR, 2) sweep2_kernel(const SweepArgs a) {
                 c2 = fma(rr, rr, c2);
             }
             c2 = warp_sum(c2) + ctl.c0;
-            const double S = (sm[LY::o_sred + u] + sm[LY::o_sred + 8 + u]) + (sm[LY::o_sred + 16 + u] + sm[LY::o_sred + 24 + u]);
+            const double* sr = sm + LY::o_sred + u;
+            const double S = ((sr[0] + sr[8]) + (sr[16] + sr[24])) + ((sr[32] + sr[40]) + (sr[48] + sr[56]));
             if (lane == 0) {
                 ctl.uchi2[u] = c2; ctl.uS[u] = S;
                 ctl.uQ[u] = ctl.ufail[u] ? nan("") : 0.5 * c2 * a.eta - ctl.alpha * S;   // maxent_cost_function.py:82
@@ -729,45 +747,48 @@ __global__ void __launch_bounds__(NTHR, 2) sweep2_kernel(const SweepArgs a) {
 
     auto shift_of = [&](int i, double mu) -> double { return bryan ? mu / sm[LY::o_lam + i] : mu; };
 
-    // ---- P3: factorise J + shift(mu_u) and solve for every unique trial (one warp per matrix) -------------
+    // ---- P3: factorise J + shift(mu_u) and solve for every unique trial (one solver warp per matrix) -------
     auto solve_trials = [&]() {
         const int nuniq = ctl.nuniq;
-        for (int u = warp; u < nuniq; u += NWARP) {
-            const double mu = ctl.umu[u];
-            double A[NTRI][2];
+        regs_to_solvers();
+        if (warp < NSOLVE) {
+            for (int u = warp; u < nuniq; u += NSOLVE) {
+                const double mu = ctl.umu[u];
+                double A[NTRI][2];
 #pragma unroll
-            for (int t = 0; t < NTRI; ++t) {
-                const double2 v = *reinterpret_cast<const double2*>(sm + LY::o_J + t * 64 + 2 * lane);
-                A[t][0] = v.x; A[t][1] = v.y;
-            }
-#pragma unroll
-            for (int I = 0; I < NT; ++I) {
-                const int i0 = 8 * I + r;
-                if (i0 < s) {
-                    const double sh = shift_of(i0, mu);
-                    if (r == 2 * q) A[tri(I, I)][0] += sh;
-                    if (r == 2 * q + 1) A[tri(I, I)][1] += sh;
+                for (int t = 0; t < NTRI; ++t) {
+                    const double2 v = *reinterpret_cast<const double2*>(sm + LY::o_J + t * 64 + 2 * lane);
+                    A[t][0] = v.x; A[t][1] = v.y;
                 }
-            }
-            double U[NT][2];
-            bool ok = true;
-            double ld = 0.0;
-            chol_steps<NT, 0>(A, U, ok, ld, false, r, q, lane);
-            ok = __all_sync(0xffffffffu, ok);
-            double xr[NT];
-            chol_solve<NT>(A, U, sm + LY::o_rhs, xr, r);
-            if (q == 0) {
 #pragma unroll
                 for (int I = 0; I < NT; ++I) {
                     const int i0 = 8 * I + r;
-                    const double dv = ok ? xr[I] : 0.0;
-                    sm[LY::o_dvb + u * SP + i0] = dv;
-                    sm[LY::o_tb + u * SP + i0] = ok ? sm[LY::o_v + i0] - dv : 0.0;
+                    if (i0 < s) {
+                        const double sh = shift_of(i0, mu);
+                        if (r == 2 * q) A[tri(I, I)][0] += sh;
+                        if (r == 2 * q + 1) A[tri(I, I)][1] += sh;
+                    }
                 }
+                double U[NT][2];
+                bool ok = true;
+                double ld = 0.0;
+                chol_steps<NT, 0>(A, U, ok, ld, false, r, q, lane);
+                ok = __all_sync(0xffffffffu, ok);
+                double xr[NT];
+                chol_solve<NT>(A, U, sm + LY::o_rhs, xr, r, q, sm + LY::o_dvb + u * SP);
+                if (q == 0) {
+#pragma unroll
+                    for (int I = 0; I < NT; ++I) {
+                        const int i0 = 8 * I + r;
+                        const double dv = ok ? xr[I] : 0.0;
+                        sm[LY::o_dvb + u * SP + i0] = dv;
+                        sm[LY::o_tb + u * SP + i0] = ok ? sm[LY::o_v + i0] - dv : 0.0;
+                    }
+                }
+                if (lane == 0) ctl.ufail[u] = ok ? 0 : 1;
             }
-            if (lane == 0) ctl.ufail[u] = ok ? 0 : 1;
         }
-        __syncthreads();
+        regs_back();
     };
 
     // ---- log det(I + eta Xi Z Xi / alpha) by warp 0 (probabilities.py:76-85 via Sylvester) -----------------
@@ -847,23 +868,25 @@ __global__ void __launch_bounds__(NTHR, 2) sweep2_kernel(const SweepArgs a) {
                 if (!ctl.action) break;
                 // ---- this alpha is finished: probability, outputs ----
                 const size_t o = (size_t)sp * a.n_alpha + ctl.ia;
-                if (warp == 0) {
-                    double logp = nan("");
-                    if (a.want_prob) {
+                if (a.want_prob) {                             // the factorisation needs the solver register budget
+                    regs_to_solvers();
+                    if (warp == 0) {
                         const double ld = logdet_prob();
-                        logp = -0.5 * ld - ctl.lm.Q1 - log(ctl.alpha);
+                        if (lane == 0) ctl.pq[0] = ld;
                     }
-                    if (lane == 0) {
-                        const bool hit_max = ctl.it >= a.maxiter;
-                        a.o_chi2[o] = ctl.chi2_cur;
-                        a.o_S[o] = ctl.S_cur;
-                        a.o_Q[o] = ctl.lm.Q1;
-                        if (a.o_logp) a.o_logp[o] = logp;
-                        if (a.o_niter) a.o_niter[o] = hit_max ? a.maxiter : ctl.it + 1;
-                        if (a.o_nq) a.o_nq[o] = ctl.nq;
-                        if (a.o_ns) a.o_ns[o] = ctl.ns;
-                        if (a.o_status) a.o_status[o] = (!hit_max && ctl.conv) ? MX_STATUS_CONVERGED : 0;
-                    }
+                    regs_back();
+                }
+                if (tid == 0) {
+                    const double logp = a.want_prob ? -0.5 * ctl.pq[0] - ctl.lm.Q1 - log(ctl.alpha) : nan("");
+                    const bool hit_max = ctl.it >= a.maxiter;
+                    a.o_chi2[o] = ctl.chi2_cur;
+                    a.o_S[o] = ctl.S_cur;
+                    a.o_Q[o] = ctl.lm.Q1;
+                    if (a.o_logp) a.o_logp[o] = logp;
+                    if (a.o_niter) a.o_niter[o] = hit_max ? a.maxiter : ctl.it + 1;
+                    if (a.o_nq) a.o_nq[o] = ctl.nq;
+                    if (a.o_ns) a.o_ns[o] = ctl.ns;
+                    if (a.o_status) a.o_status[o] = (!hit_max && ctl.conv) ? MX_STATUS_CONVERGED : 0;
                 }
                 if (a.o_v) for (int i = tid; i < s; i += NTHR) a.o_v[o * s + i] = sm[LY::o_v + i];
                 if (a.o_A) {                                   // A = H / delta  (functions.py:947-952)

@@ -50,7 +50,7 @@ class SharedProblem(object):
     this rotation because mu*1 is."""
 
     def __init__(self, K, err, D, delta, variant="normal", reduce_singular_space=1.e-14, device=None,
-                 svd="jacobi", A_init=None, max_nsv=None, engine=0, rank_floor=1.e-14):
+                 svd="jacobi", A_init=None, max_nsv=None, engine=0, rank_floor=5.e-16):
         torch = _torch()
         if not torch.cuda.is_available():
             raise _lib.MaxEntLibraryError("maxent_b200 needs a CUDA device (no CPU fallback)")

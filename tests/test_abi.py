@@ -67,7 +67,7 @@ def test_introspection_calls_without_gpu(lib):
     from maxent_b200 import _lib
     for s in (8, 32, 47, 52, 64):
         cfg = _lib.sweep_config(s)
-        assert cfg["engine"] == _lib.ENGINE_SPECTRUM_CTA and cfg["spectra_per_cta"] == 1 and cfg["threads"] == 128
+        assert cfg["engine"] == _lib.ENGINE_SPECTRUM_CTA and cfg["spectra_per_cta"] == 1 and cfg["threads"] == 256
         assert 2 * cfg["smem_bytes"] <= 227 * 1024           # two CTAs per SM
         cfg = _lib.sweep_config(s, _lib.ENGINE_LOCKSTEP)
         assert 1 <= cfg["spectra_per_cta"] <= 8 and cfg["smem_bytes"] <= 227 * 1024
