@@ -99,6 +99,16 @@ __device__ __forceinline__ double rsqrt_nr(double a) {
     return fma(h, e, y);
 }
 
+// 1/a: MUFU.RCP64H seed + two Newton steps
+__device__ __forceinline__ double rcp_nr(double a) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double e = fma(-a, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-a, y, 1.0);
+    return fma(y, e, y);
+}
+
 // c += X Y^T for two 8x8 tiles in C layout (k permuted: k-step e uses columns 2q+e)
 __device__ __forceinline__ void mma_nt(double (&c)[2], double x0, double x1, double y0, double y1) {
     dmma(c, x0, y0);
@@ -159,7 +169,8 @@ struct Ctl {
     int urow[NROWS];           // scratch row of each unique trial (8 = carried)
     int ufail[NROWS];
     int nb, nuniq;
-    int spec, ia, it, nq, ns, dir_up, cur_row, action, conv;
+    double jdmin;              // smallest |J_kk| (quick test for equivalent dampings)
+    int spec, ia, it, nq, ns, dir_up, cur_row, action, conv, last_len, ns_it0;
     unsigned gchunk;           // chunks streamed so far (pipeline phase bookkeeping)
 };
 static_assert(sizeof(Ctl) <= 192 * sizeof(double), "Ctl must fit its reserved block");
@@ -229,19 +240,22 @@ __device__ __forceinline__ void chol_panel(double (&A)[Lay<NT>::NTRI][2], double
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int jq = j >> 1, je = j & 1;
+        // The trailing update uses the UNSCALED column j and 1/a_jj, so the next pivot depends only on the short
+        // reciprocal chain; 1/sqrt(a_jj), which only the final values of column j need, runs beside it.
         const double ajj = shfl(P0[je], 4 * j + jq);
+        const double lk0 = shfl(P0[je], 8 * q + jq);              // a[2q][j]
+        const double lk1 = shfl(P0[je], 8 * q + 4 + jq);          // a[2q+1][j]
+        const int src = (lane & ~3) | jq;
+        const double lp = shfl(P0[je], src);                      // a[r][j]
+        const double le = shfl(E[je], src);
         if (!(ajj > 0.0)) ok = false;
         if (want_logdet) logdet += log(ajj);
+        const double inv = rcp_nr(ajj);
         const double rinv = rsqrt_nr(ajj);
-        if (q == jq) { P0[je] *= rinv; E[je] *= rinv; }          // scale column j
-        const double lk0 = shfl(P0[je], 8 * q + jq);              // L_d[2q][j]
-        const double lk1 = shfl(P0[je], 8 * q + 4 + jq);          // L_d[2q+1][j]
-        const bool u0 = (2 * q > j), u1 = (2 * q + 1 > j);
-        const int src = (lane & ~3) | jq;
-        const double lp = shfl(P0[je], src);
-        const double le = shfl(E[je], src);
-        if (u0) { P0[0] = fma(-lp, lk0, P0[0]); E[0] = fma(-le, lk0, E[0]); }
-        if (u1) { P0[1] = fma(-lp, lk1, P0[1]); E[1] = fma(-le, lk1, E[1]); }
+        const double p0 = lp * lk0, p1 = lp * lk1, e0 = le * lk0, e1 = le * lk1;
+        if (2 * q > j) { P0[0] = fma(-p0, inv, P0[0]); E[0] = fma(-e0, inv, E[0]); }
+        if (2 * q + 1 > j) { P0[1] = fma(-p1, inv, P0[1]); E[1] = fma(-e1, inv, E[1]); }
+        if (q == jq) { P0[je] *= rinv; E[je] *= rinv; }          // final values of column j
     }
     if (r < 2 * q) P0[0] = 0.0;
     if (r < 2 * q + 1) P0[1] = 0.0;
@@ -743,6 +757,13 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
             *reinterpret_cast<double2*>(sm + LY::o_J + t * 64 + 2 * lane) = make_double2(c[0], c[1]);
         }
         __syncthreads();
+        if (warp == 0) {                                       // smallest |J_kk| for the planner's equivalence pre-test
+            double m = INFINITY;
+            for (int k = lane; k < s; k += 32) m = fmin(m, fabs(sm[LY::o_jd + k]));
+            m = -warp_max(-m);
+            if (lane == 0) ctl.jdmin = m;
+        }
+        __syncthreads();
     };
 
     auto shift_of = [&](int i, double mu) -> double { return bryan ? mu / sm[LY::o_lam + i] : mu; };
@@ -838,7 +859,7 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
             sm[LY::o_tb + i] = (b == 0 && j < s) ? a.v0[j] : 0.0;
         }
         if (tid == 0) {
-            ctl.ia = 0; ctl.it = 0; ctl.nq = 0; ctl.ns = 0; ctl.dir_up = 1;
+            ctl.ia = 0; ctl.it = 0; ctl.nq = 0; ctl.ns = 0; ctl.dir_up = 1; ctl.last_len = 99;
             ctl.alpha = a.alpha[0]; ctl.c0 = a.c0[sp];
             ctl.lm.mu = a.mu0; ctl.lm.Q0 = nan(""); ctl.lm.phase = PH_FIRST;
             ctl.nuniq = 1; ctl.nb = 0; ctl.urow[0] = 0; ctl.ufail[0] = 0;
@@ -898,7 +919,7 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                     ctl.ia++;
                     if (ctl.ia < a.n_alpha) {
                         ctl.alpha = a.alpha[ctl.ia];
-                        ctl.lm.mu = a.mu0; ctl.lm.Q0 = nan(""); ctl.it = 0; ctl.nq = 1; ctl.ns = 0; ctl.dir_up = 1;
+                        ctl.lm.mu = a.mu0; ctl.lm.Q0 = nan(""); ctl.it = 0; ctl.nq = 1; ctl.ns = 0; ctl.dir_up = 1; ctl.last_len = 99;
                     }
                 }
                 __syncthreads();
@@ -907,24 +928,33 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
             if (spectrum_done) break;
             form_J();
             // ---- one Levenberg iteration: speculative batches until the damping search is decided ----
-            if (tid == 0) { ctl.lm.Q0 = ctl.lm.Q1; ctl.lm.phase = PH_FIRST; ctl.nb = 0; ctl.nuniq = 0; ctl.urow[ID_CARRY] = -1; }
+            if (tid == 0) { ctl.lm.Q0 = ctl.lm.Q1; ctl.lm.phase = PH_FIRST; ctl.nb = 0; ctl.nuniq = 0; ctl.urow[ID_CARRY] = -1; ctl.ns_it0 = ctl.ns; }
             __syncthreads();
             for (;;) {
                 if (warp == 0) {
-                    // The whole warp runs the (scalar, warp-uniform) state machine so that table searches and the
-                    // "same shifted diagonal" tests are ballots instead of serial loops.
+                    // The whole warp runs the (scalar, warp-uniform) state machine.  The tables live in registers:
+                    // lane i holds table entry i (damping, unique trial) and unique trial i (damping, Q, failed);
+                    // searches are ballots, reads are shuffles.
                     LM L = ctl.lm;
                     int ns = ctl.ns, nq = ctl.nq;
                     const double* jdv = sm + LY::o_jd;
-                    // two dampings are equivalent when they give bitwise the same matrix J + shift(mu)
-                    double jdmin = INFINITY;
-                    for (int k = lane; k < s; k += 32) jdmin = fmin(jdmin, fabs(jdv[k]));
-                    jdmin = -warp_max(-jdmin);
-                    auto equiv = [&](double ma, double mb) -> bool {
+                    const double jdmin = ctl.jdmin;
+                    const int nb0 = ctl.nb, nu0 = ctl.nuniq;
+                    int carry_row = ctl.urow[ID_CARRY];
+                    double t_mu = lane < nb0 ? ctl.bmu[lane] : 0.0;
+                    int t_slot = lane < nb0 ? ctl.bslot[lane] : 0;
+                    const bool uvalid = lane < nu0 || (lane == ID_CARRY && carry_row >= 0);
+                    double u_mu = uvalid ? ctl.umu[lane] : 0.0;
+                    double u_Q = uvalid ? ctl.uQ[lane] : 0.0;
+                    int u_fail = uvalid ? ctl.ufail[lane] : 0;
+                    // two dampings are equivalent when they give bitwise the same matrix J + shift(mu).  The entry
+                    // with the smallest |J_kk| can only round to the same value if they differ by less than two of
+                    // its ulps: cheap per-lane pre-test, the full comparison is rarely reached
+                    auto maybe = [&](double ma, double mb) -> bool {
+                        return ma == mb || bryan || !(fabs(ma - mb) > 4.5e-16 * (jdmin + fmax(ma, mb)));
+                    };
+                    auto equiv_full = [&](double ma, double mb) -> bool {
                         if (ma == mb) return true;
-                        // the entry with the smallest |J_kk| can only round to the same value if the dampings
-                        // differ by less than two of its ulps: cheap exit for everything but vanishing dampings
-                        if (!bryan && fabs(ma - mb) > 4.5e-16 * (jdmin + fmax(ma, mb))) return false;
                         bool same = true;
                         for (int k = lane; k < s; k += 32) {
                             const double jd = jdv[k];
@@ -932,18 +962,22 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                         }
                         return __all_sync(0xffffffffu, same);
                     };
-                    const int nb0 = ctl.nb, nu0 = ctl.nuniq;
                     auto look_real = [&](double mu, int, double, double& Q, int& id) -> bool {
-                        const unsigned m = __ballot_sync(0xffffffffu, lane < nb0 && ctl.bmu[lane] == mu);
+                        const unsigned m = __ballot_sync(0xffffffffu, lane < nb0 && t_mu == mu);
                         id = -1;
-                        if (m) id = ctl.bslot[__ffs(m) - 1];
+                        if (m) id = __shfl_sync(0xffffffffu, t_slot, __ffs(m) - 1);
                         else {
-                            for (int u = 0; u < nu0 && id < 0; ++u) if (equiv(mu, ctl.umu[u])) id = u;
-                            if (id < 0 && ctl.urow[ID_CARRY] >= 0 && equiv(mu, ctl.umu[ID_CARRY])) id = ID_CARRY;
+                            const bool have_c = carry_row >= 0;
+                            unsigned cm = __ballot_sync(0xffffffffu, (lane < nu0 || (lane == ID_CARRY && have_c)) && maybe(mu, u_mu));
+                            while (cm && id < 0) {
+                                const int u = __ffs(cm) - 1;
+                                cm &= cm - 1;
+                                if (equiv_full(mu, shfl(u_mu, u))) id = u;
+                            }
                         }
                         if (id < 0) return false;
-                        Q = ctl.uQ[id];
-                        ++ns; if (!ctl.ufail[id]) ++nq;
+                        Q = shfl(u_Q, id);
+                        ++ns; if (!__shfl_sync(0xffffffffu, u_fail, id)) ++nq;
                         return true;
                     };
                     const int done = lm_run(L, a.nu, a.max_mu, eps_nu, look_real) ? 1 : 0;
@@ -955,51 +989,67 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                                 sm[LY::o_cdv + i] = sm[LY::o_dvb + live * SP + i];
                                 sm[LY::o_cy + i] = sm[LY::o_yb + live * SP + i];
                             }
-                            if (lane == 0) {
-                                ctl.uQ[ID_CARRY] = ctl.uQ[live]; ctl.uchi2[ID_CARRY] = ctl.uchi2[live]; ctl.uS[ID_CARRY] = ctl.uS[live];
-                                ctl.ufail[ID_CARRY] = ctl.ufail[live]; ctl.urow[ID_CARRY] = ctl.urow[live];
-                                ctl.umu[ID_CARRY] = ctl.umu[live];
+                            const double lmu = shfl(u_mu, live), lQ = shfl(u_Q, live);
+                            const int lfail = __shfl_sync(0xffffffffu, u_fail, live);
+                            carry_row = ctl.urow[live];
+                            if (lane == ID_CARRY) {
+                                u_mu = lmu; u_Q = lQ; u_fail = lfail;
+                                ctl.uQ[ID_CARRY] = lQ; ctl.uchi2[ID_CARRY] = ctl.uchi2[live]; ctl.uS[ID_CARRY] = ctl.uS[live];
+                                ctl.ufail[ID_CARRY] = lfail; ctl.urow[ID_CARRY] = carry_row; ctl.umu[ID_CARRY] = lmu;
                             }
                             if (L.phase == PH_WALK) L.dvnew = ID_CARRY; else L.dv = ID_CARRY;
                         } else if (live == ID_NONE) {
+                            carry_row = -1;
                             if (lane == 0) ctl.urow[ID_CARRY] = -1;
                         }
                         __syncwarp();
-                        // plan: continue a copy of the machine with pretended outcomes to list the next dampings
+                        // plan: continue a copy of the machine with pretended outcomes to list the next dampings.
+                        // Width: four unique trials (one solver round) when the previous iteration was short and
+                        // this is the first batch of the iteration, else eight.
                         LM P = L;
                         int np = 0, npu = 0;
+                        const int maxu = (ns == ctl.ns_it0 && ctl.last_len <= 4 && L.phase == PH_FIRST) ? 4 : MAXB;
                         const bool dir_up = ctl.dir_up != 0;
-                        const bool have_carry = ctl.urow[ID_CARRY] >= 0;
-                        const double cmu = ctl.umu[ID_CARRY];
+                        const bool have_carry = carry_row >= 0;
+                        const double cmu = shfl(u_mu, ID_CARRY), cQ = shfl(u_Q, ID_CARRY);
+                        double p_mu = 0.0, pu_mu = 0.0, pu_q = 0.0;       // planned table entry / unique trial of this lane
+                        int p_slot = 0;
                         auto look_plan = [&](double mu, int kind, double Qref, double& Q, int& id) -> bool {
-                            if (have_carry && equiv(mu, cmu)) { Q = ctl.uQ[ID_CARRY]; id = ID_CARRY; return true; }
-                            const unsigned m = __ballot_sync(0xffffffffu, lane < np && ctl.bmu[lane] == mu);
-                            if (m) { const int u = ctl.bslot[__ffs(m) - 1]; Q = ctl.pq[u]; id = 100 + u; return true; }
-                            for (int u = 0; u < npu; ++u)
-                                if (equiv(mu, ctl.umu[u])) {
-                                    if (np < NTAB) { if (lane == 0) { ctl.bmu[np] = mu; ctl.bslot[np] = u; } ++np; __syncwarp(); }
-                                    Q = ctl.pq[u]; id = 100 + u;
+                            if (have_carry && maybe(mu, cmu) && equiv_full(mu, cmu)) { Q = cQ; id = ID_CARRY; return true; }
+                            const unsigned m = __ballot_sync(0xffffffffu, lane < np && p_mu == mu);
+                            if (m) {
+                                const int u = __shfl_sync(0xffffffffu, p_slot, __ffs(m) - 1);
+                                Q = shfl(pu_q, u); id = 100 + u;
+                                return true;
+                            }
+                            unsigned cm = __ballot_sync(0xffffffffu, lane < npu && maybe(mu, pu_mu));
+                            while (cm) {
+                                const int u = __ffs(cm) - 1;
+                                cm &= cm - 1;
+                                if (equiv_full(mu, shfl(pu_mu, u))) {
+                                    if (np < NTAB) { if (lane == np) { p_mu = mu; p_slot = u; } ++np; }
+                                    Q = shfl(pu_q, u); id = 100 + u;
                                     return true;
                                 }
-                            if (npu == MAXB || np == NTAB) return false;
+                            }
+                            if (npu == maxu || np == NTAB) return false;
                             double pv;
                             if (kind == 0) pv = isnan(Qref) ? 0.0 : Qref;                        // first trial / pump: "accepted"
                             else if (kind == 1) pv = dir_up ? Qref - (1.0 + fabs(Qref)) : Qref + (1.0 + fabs(Qref));
                             else pv = Qref - (1.0 + fabs(Qref));                                  // walk: "still improving"
-                            if (lane == 0) { ctl.bmu[np] = mu; ctl.bslot[np] = npu; ctl.umu[npu] = mu; ctl.pq[npu] = pv; }
+                            if (lane == np) { p_mu = mu; p_slot = npu; }
+                            if (lane == npu) { pu_mu = mu; pu_q = pv; }
                             id = 100 + npu; Q = pv; ++np; ++npu;
-                            __syncwarp();
                             return true;
                         };
                         lm_run(P, a.nu, a.max_mu, eps_nu, look_plan);
-                        if (lane == 0) {
-                            ctl.nb = np; ctl.nuniq = npu;
-                            int rowp = 0;
-                            for (int u = 0; u < npu; ++u) {
-                                if (rowp == ctl.urow[ID_CARRY]) ++rowp;
-                                ctl.urow[u] = rowp++; ctl.ufail[u] = 0;
-                            }
+                        if (lane < np) { ctl.bmu[lane] = p_mu; ctl.bslot[lane] = p_slot; }
+                        if (lane < npu) {
+                            ctl.umu[lane] = pu_mu;
+                            ctl.urow[lane] = (carry_row >= 0 && lane >= carry_row) ? lane + 1 : lane;   // skip the carried row
+                            ctl.ufail[lane] = 0;
                         }
+                        if (lane == 0) { ctl.nb = np; ctl.nuniq = npu; }
                     }
                     if (lane == 0) { ctl.lm = L; ctl.ns = ns; ctl.nq = nq; ctl.conv = done; }
                 }
@@ -1024,6 +1074,7 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                     ctl.it++;
                     ctl.nq++;                                    // the reference re-evaluates func_val = function(v)
                     ctl.dir_up = (ctl.lm.nuf == a.nu) ? 1 : 0;
+                    ctl.last_len = ctl.ns - ctl.ns_it0;
                 }
                 __syncthreads();
             }

@@ -70,11 +70,39 @@ def panel(tiles, E):
     return ok, logdet
 
 
+def panel_unnormalized(P0, E):
+    """Column steps as in chol_panel of mx_sweep2.cuh: the trailing update uses the UNSCALED column and 1/a_jj,
+    so that the reciprocal square root (needed only for the final L values) is off the critical path."""
+    ok = True
+    logdet = 0.0
+    for j in range(8):
+        jq, je = j >> 1, j & 1
+        ajj = shfl(P0[je], np.full(32, 4 * j + jq))
+        if not np.all(ajj > 0):
+            ok = False
+        logdet += np.log(ajj[0])
+        lk0 = shfl(P0[je], 4 * (2 * Qn) + jq)
+        lk1 = shfl(P0[je], 4 * (2 * Qn + 1) + jq)
+        lp = shfl(P0[je], 4 * R + jq)
+        le = shfl(E[je], 4 * R + jq)
+        inv = 1.0 / ajj
+        rinv = 1.0 / np.sqrt(ajj)
+        P0[0] = np.where(2 * Qn > j, P0[0] - (lp * lk0) * inv, P0[0])
+        P0[1] = np.where(2 * Qn + 1 > j, P0[1] - (lp * lk1) * inv, P0[1])
+        E[0] = np.where(2 * Qn > j, E[0] - (le * lk0) * inv, E[0])
+        E[1] = np.where(2 * Qn + 1 > j, E[1] - (le * lk1) * inv, E[1])
+        P0[je] = np.where(Qn == jq, P0[je] * rinv, P0[je])
+        E[je] = np.where(Qn == jq, E[je] * rinv, E[je])
+    P0[0] = np.where(R >= 2 * Qn, P0[0], 0.0)
+    P0[1] = np.where(R >= 2 * Qn + 1, P0[1], 0.0)
+    return ok, logdet
+
+
 def panel_w(tiles, E):
     """The variant used by mx_sweep2.cuh: column steps on the diagonal tile and the identity tile only, then
     L[I][JB] = A[I][JB] W^T through two MMAs per tile with W = U^T (in-register transpose)."""
     P0 = tiles[0]
-    ok, logdet = panel([P0], E)
+    ok, logdet = panel_unnormalized(P0, E)
     s0 = 8 * Qn + (R >> 1)
     s1 = s0 + 4
     a0, b0 = shfl(E[0], s0), shfl(E[1], s0)
