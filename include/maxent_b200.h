@@ -144,12 +144,15 @@ int mx_sweep_config(int32_t n_sv, int32_t engine, int32_t* engine_used, int32_t*
                     int32_t* smem_bytes, int32_t* threads);
 
 /* Analyzer reductions (python/analyzers/*.py) for B spectra:
- * alpha_index[B, MX_N_ANALYZERS] (-1 = not available), A_out[B, MX_N_ANALYZERS, n_omega]. */
+ * alpha_index[B, MX_N_ANALYZERS] (-1 = not available), A_out[B, MX_N_ANALYZERS, n_omega] (may be NULL),
+ * aux[B, 4 + 2 n_alpha] (may be NULL): the line-fit parameters {slope1, intercept1, slope2, intercept2}
+ * (linefit_analyzer.py:63-69), curvature[n_alpha] (chi2_curvature_analyzer.py:25-49) and
+ * dS/dlog(alpha)[n_alpha] (entropy_analyzer.py:92-95); entries that do not exist are NaN. */
 int mx_analyze(const double* alpha /*[n_alpha]*/, const double* chi2, const double* S,
                const double* logp /* may be NULL */, const double* A /*[B, n_alpha, n_omega]*/,
                int32_t B, int32_t n_alpha, int32_t n_omega, double gamma, int32_t linefit_deg,
                int32_t bryan_by_integration,
-               int32_t* alpha_index, double* A_out, void* stream);
+               int32_t* alpha_index, double* A_out, double* aux, void* stream);
 
 #ifdef __cplusplus
 }

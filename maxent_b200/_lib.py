@@ -62,7 +62,7 @@ SYMBOLS = [
                                        ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
                                        ctypes.POINTER(ctypes.c_int32)]),
     ("mx_analyze", ctypes.c_int, [c_dp, c_dp, c_dp, c_dp, c_dp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
-                                  ctypes.c_double, ctypes.c_int32, ctypes.c_int32, c_dp, c_dp, c_dp]),
+                                  ctypes.c_double, ctypes.c_int32, ctypes.c_int32, c_dp, c_dp, c_dp, c_dp]),
 ]
 
 _lib = None

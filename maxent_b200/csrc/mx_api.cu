@@ -94,7 +94,8 @@ __global__ void __launch_bounds__(128) analyze_kernel(const double* __restrict__
                                                       const double* __restrict__ S, const double* __restrict__ logp,
                                                       const double* __restrict__ A, int n_alpha, int n_omega,
                                                       double gamma, int linefit_deg, int by_integration,
-                                                      int* __restrict__ aidx, double* __restrict__ A_out) {
+                                                      int* __restrict__ aidx, double* __restrict__ A_out,
+                                                      double* __restrict__ aux) {
     extern __shared__ double sh[];
     double* lx = sh;                    // log alpha
     double* ly = lx + n_alpha;          // log chi2
@@ -105,6 +106,9 @@ __global__ void __launch_bounds__(128) analyze_kernel(const double* __restrict__
     const double* c2 = chi2 + (int64_t)b * n_alpha;
     const double* Sb = S + (int64_t)b * n_alpha;
     const double* pb = logp ? logp + (int64_t)b * n_alpha : nullptr;
+    // aux row: [0..3] line-fit parameters (slope, intercept of both pieces), then curvature[n_alpha], dS/dlog(alpha)[n_alpha]
+    double* ax = aux ? aux + (int64_t)b * (4 + 2 * n_alpha) : nullptr;
+    if (ax) for (int i = tid; i < 4 + 2 * n_alpha; i += blockDim.x) ax[i] = nan("");
     for (int i = tid; i < n_alpha; i += blockDim.x) { lx[i] = log(alpha[i]); ly[i] = log(c2[i]); cost[i] = nan(""); }
     if (tid < MX_N_ANALYZERS) idx[tid] = -1;
     __syncthreads();
@@ -128,6 +132,7 @@ __global__ void __launch_bounds__(128) analyze_kernel(const double* __restrict__
             int k = -1; double kv = 0;
             for (int i = 0; i < n_alpha; ++i) { const double d = fabs(lx[i] - X); if (!isnan(d) && (k < 0 || d < kv)) { k = i; kv = d; } }
             idx[MX_AN_LINEFIT] = k;
+            if (ax) { ax[0] = m1; ax[1] = c1; ax[2] = (linefit_deg == 1 ? m2 : 0.0); ax[3] = c2_; }
         }
         (void)p1s;
     }
@@ -141,6 +146,7 @@ __global__ void __launch_bounds__(128) analyze_kernel(const double* __restrict__
             const double d2 = (y2 - 2 * y1 + y0) / ((x2 - x1) * (x1 - x0));
             const double d1 = ((y2 - y1) / (x2 - x1) + (y1 - y0) / (x1 - x0)) / 2;
             const double cv = d2 / pow(1 + d1 * d1, 1.5);
+            if (ax) ax[4 + i] = cv;
             if (!isnan(cv) && (k < 0 || cv > kv)) { k = i; kv = cv; }
         }
         (void)il10;
@@ -152,6 +158,7 @@ __global__ void __launch_bounds__(128) analyze_kernel(const double* __restrict__
         for (int i = 1; i < n_alpha - 1; ++i) {
             const double d = (Sb[i + 1] - Sb[i - 1]) / (log(alpha[i + 1]) - log(alpha[i - 1]));
             const double v = d * d;
+            if (ax) ax[4 + n_alpha + i] = d;
             if (!isnan(v) && (k < 0 || v < kv)) { k = i; kv = v; }
         }
         idx[MX_AN_ENTROPY] = k;
@@ -340,12 +347,12 @@ int mx_alpha_sweep(const MxProblem* p, const double* gt, const double* c0, int32
 
 int mx_analyze(const double* alpha, const double* chi2, const double* S, const double* logp, const double* A,
                int32_t B, int32_t n_alpha, int32_t n_omega, double gamma, int32_t linefit_deg,
-               int32_t bryan_by_integration, int32_t* alpha_index, double* A_out, void* stream) {
+               int32_t bryan_by_integration, int32_t* alpha_index, double* A_out, double* aux, void* stream) {
     if (B == 0) return MX_OK;
     if (!alpha || !chi2 || !S || !alpha_index || B < 0 || n_alpha < 1 || n_alpha > 1024) return MX_ERR_BAD_ARG;
     const size_t shb = 4 * (size_t)n_alpha * sizeof(double);
     analyze_kernel<<<B, 128, shb, (cudaStream_t)stream>>>(alpha, chi2, S, logp, A, n_alpha, n_omega, gamma,
-                                                          linefit_deg, bryan_by_integration, alpha_index, A_out);
+                                                          linefit_deg, bryan_by_integration, alpha_index, A_out, aux);
     return cudaGetLastError() == cudaSuccess ? MX_OK : MX_ERR_CUDA;
 }
 

@@ -50,7 +50,11 @@ class SharedProblem(object):
     this rotation because mu*1 is."""
 
     def __init__(self, K, err, D, delta, variant="normal", reduce_singular_space=1.e-14, device=None,
-                 svd="jacobi", A_init=None, max_nsv=None, engine=0, rank_floor=5.e-16):
+                 svd="jacobi", A_init=None, max_nsv=None, engine=0, rank_floor=5.e-16, usv=None,
+                 orthonormal_U=True):
+        """``usv`` = (U, S, V) already truncated by the caller (a ``kernels.KernelSVD`` after
+        ``reduce_singular_space``); ``orthonormal_U=False`` when U was rotated by a non-square T
+        (TauMaxEnt.set_cov with dropped eigenvalues), which forces the general whitening branch."""
         torch = _torch()
         if not torch.cuda.is_available():
             raise _lib.MaxEntLibraryError("maxent_b200 needs a CUDA device (no CPU fallback)")
@@ -65,7 +69,12 @@ class SharedProblem(object):
             self.n_tau, self.n_omega = int(n_tau), int(n_omega)
             self.variant = variant
             # ---- SVD of the kernel (KernelSVD.svd, python/kernels.py:53-64) ----
-            U, S, V = self._svd(K, svd)
+            if usv is not None:
+                U, S, V = [torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64) if not torch.is_tensor(x) else x,
+                                           dtype=f64, device=dev).contiguous() for x in usv]
+                reduce_singular_space, rank_floor = None, 0.0          # the caller has applied its cut
+            else:
+                U, S, V = self._svd(K, svd)
             # reduce_singular_space is an ABSOLUTE threshold (python/kernels.py:101-122).  Below
             # rank_floor * S[0] the computed singular triplets are rounding noise (which of them pass an absolute
             # 1e-14 depends on the SVD implementation, and their left vectors are not orthonormal any more), so the
@@ -87,12 +96,11 @@ class SharedProblem(object):
             err_np = np.asarray(err, dtype=np.float64) * np.ones(self.n_tau)
             err_t = torch.as_tensor(err_np, dtype=f64, device=dev)
             sqrtw = 1.0 / err_t
-            if np.all(err_np == err_np[0]):
+            if orthonormal_U and np.all(err_np == err_np[0]):
                 Q, Xi, P = U, S / err_np[0], None
             else:
-                M = sqrtw[:, None] * (K @ V)
-                Q, Xi, Pt = torch.linalg.svd(M, full_matrices=False)
-                P = Pt.transpose(0, 1).contiguous()
+                M = (sqrtw[:, None] * (K @ V)).contiguous()
+                Q, Xi, P = self._svd(M, svd)
             self.P = P
             self.Vp = V if P is None else (V @ P).contiguous()
             self.Q = Q.contiguous()
@@ -121,6 +129,8 @@ class SharedProblem(object):
 
     def _svd(self, K, method):
         torch = _torch()
+        if not hasattr(self, "svd_sweeps"):
+            self.svd_sweeps = None
         if method == "jacobi":
             m, n = K.shape
             tr = m < n
@@ -134,7 +144,8 @@ class SharedProblem(object):
             stream = ctypes.c_void_p(torch.cuda.current_stream(K.device).cuda_stream)
             _lib.check(self.lib.mx_svd_jacobi(_ptr(Kk), m2, n2, _ptr(U), _ptr(S), _ptr(V), _ptr(work), 60,
                                               ctypes.byref(sweeps), stream), "mx_svd_jacobi")
-            self.svd_sweeps = sweeps.value
+            if self.svd_sweeps is None:
+                self.svd_sweeps = sweeps.value
             return (V, S, U) if tr else (U, S, V)
         elif method == "torch":
             U, S, Vh = torch.linalg.svd(K, full_matrices=False)
@@ -144,6 +155,50 @@ class SharedProblem(object):
     def v_to_reference_basis(self, v):
         """v' (rotated basis) -> v in the basis of the truncated SVD of K."""
         return v if self.P is None else v @ self.P.transpose(0, 1)
+
+
+def _require_cuda():
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise _lib.MaxEntLibraryError("maxent_b200 needs a CUDA device (no CPU fallback)")
+    return torch
+
+
+def tau_kernel_host(tau, omega, beta, device=None):
+    """TauKernel values (python/kernels.py:244-266) computed by mx_tau_kernel; numpy in, numpy out."""
+    torch = _require_cuda()
+    lib = _lib.load()
+    dev = torch.device("cuda" if device is None else device)
+    with torch.cuda.device(dev):
+        t_d = torch.as_tensor(np.ascontiguousarray(tau, dtype=np.float64), device=dev)
+        o_d = torch.as_tensor(np.ascontiguousarray(omega, dtype=np.float64), device=dev)
+        K = torch.empty((t_d.numel(), o_d.numel()), dtype=torch.float64, device=dev)
+        _lib.check(lib.mx_tau_kernel(_ptr(t_d), _ptr(o_d), int(t_d.numel()), int(o_d.numel()), float(beta), _ptr(K),
+                                     _stream(dev)), "mx_tau_kernel")
+        return K.cpu().numpy()
+
+
+def svd_jacobi_host(K, device=None, max_sweeps=60):
+    """Thin SVD K = U diag(S) V^T by the device one-sided Jacobi (mx_svd_jacobi), replacing np.linalg.svd in
+    KernelSVD.svd (python/kernels.py:53-64).  numpy in, numpy (U[m,k], S[k], V[n,k]) out, k = min(m, n)."""
+    torch = _require_cuda()
+    lib = _lib.load()
+    dev = torch.device("cuda" if device is None else device)
+    with torch.cuda.device(dev):
+        Kd = torch.as_tensor(np.ascontiguousarray(K, dtype=np.float64), device=dev)
+        m, n = Kd.shape
+        tr = m < n
+        Kk = Kd.transpose(0, 1).contiguous() if tr else Kd
+        m2, n2 = Kk.shape
+        U = torch.empty((m2, n2), dtype=torch.float64, device=dev)
+        S = torch.empty((n2,), dtype=torch.float64, device=dev)
+        V = torch.empty((n2, n2), dtype=torch.float64, device=dev)
+        work = torch.empty((m2 * n2 + n2 * n2 + n2 + 8,), dtype=torch.float64, device=dev)
+        sweeps = ctypes.c_int32(0)
+        _lib.check(lib.mx_svd_jacobi(_ptr(Kk), m2, n2, _ptr(U), _ptr(S), _ptr(V), _ptr(work), int(max_sweeps),
+                                     ctypes.byref(sweeps), _stream(dev)), "mx_svd_jacobi")
+        U, S, V = U.cpu().numpy(), S.cpu().numpy(), V.cpu().numpy()
+    return (V, S, U) if tr else (U, S, V)
 
 
 class SweepResult(object):
@@ -189,10 +244,12 @@ def project_data(prob, G):
     return gt, c0
 
 
-def analyze(alpha, chi2, S, logp, A, gamma=0.2, linefit_deg=0, bryan_by_integration=False, device=None):
+def analyze(alpha, chi2, S, logp, A, gamma=0.2, linefit_deg=0, bryan_by_integration=False, device=None,
+            want_aux=False):
     """mx_analyze on arrays (python/analyzers/*.py): returns alpha_index[B, 5] (int32, -1 = not available)
-    and A_out[B, 5, n_omega] (None if A is None)."""
-    torch = _torch()
+    and A_out[B, 5, n_omega] (None if A is None); with ``want_aux`` also aux[B, 4 + 2 n_alpha]
+    (line-fit parameters, curvature, dS/dlog alpha)."""
+    torch = _require_cuda()
     lib = _lib.load()
     dev = torch.device("cuda" if device is None else device)
     if torch.is_tensor(chi2) and chi2.is_cuda:
@@ -205,9 +262,12 @@ def analyze(alpha, chi2, S, logp, A, gamma=0.2, linefit_deg=0, bryan_by_integrat
         n_omega = int(A.shape[2]) if A is not None else 0
         idx = torch.full((B, _lib.N_ANALYZERS), -1, dtype=torch.int32, device=dev)
         A_out = torch.empty((B, _lib.N_ANALYZERS, n_omega), dtype=torch.float64, device=dev) if A is not None else None
+        aux = torch.empty((B, 4 + 2 * n_alpha), dtype=torch.float64, device=dev) if want_aux else None
         _lib.check(lib.mx_analyze(_ptr(alpha), _ptr(chi2), _ptr(S), _ptr(logp), _ptr(A), B, n_alpha, n_omega,
                                   float(gamma), int(linefit_deg), int(bool(bryan_by_integration)),
-                                  _ptr(idx), _ptr(A_out), _stream(dev)), "mx_analyze")
+                                  _ptr(idx), _ptr(A_out), _ptr(aux), _stream(dev)), "mx_analyze")
+    if want_aux:
+        return idx, A_out, aux
     return idx, A_out
 
 
@@ -271,6 +331,6 @@ def run_sweep(prob, G, alpha_eff, probability=False, lm=None, chi2_factor=1.0, w
             r.A_out = torch.empty((B, _lib.N_ANALYZERS, n_omega), dtype=f64, device=dev) if want_A else None
             _lib.check(lib.mx_analyze(_ptr(alpha), _ptr(r.chi2), _ptr(r.S), _ptr(r.logp) if probability else None,
                                       _ptr(r.A), B, n_alpha, n_omega, float(gamma), int(linefit_deg),
-                                      int(bool(bryan_by_integration)), _ptr(r.alpha_index), _ptr(r.A_out), stream),
+                                      int(bool(bryan_by_integration)), _ptr(r.alpha_index), _ptr(r.A_out), None, stream),
                        "mx_analyze")
         return r

@@ -1,0 +1,273 @@
+"""GPU tests of the drop-in interface (TauMaxEnt / MaxEntLoop / ElementwiseMaxEnt ...): they read like the
+reference's own end-to-end tests (test/python/tau_maxent.py, elementwise_maxent.py, cov.py, huge_alpha.py,
+bryan_cost_function.py, pickle_maxent_result.py) and compare with the outputs of the REAL reference stored in
+tests/golden/*.npz under the tolerances of tests/gpu_common.py."""
+import pickle
+
+import numpy as np
+import pytest
+
+import maxent_b200 as mb
+from tests import gpu_common as gc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _cuda():
+    import torch
+    assert torch.cuda.is_available(), "the gpu tests need a CUDA device"
+
+
+class _ResView(object):
+    """Adapts a MaxEntResult to the tensor-like fields gc.check_against_reference reads."""
+
+    class _T(object):
+        def __init__(self, a):
+            self.a = np.asarray(a)
+
+        def __getitem__(self, i):
+            return self
+
+        def cpu(self):
+            return self
+
+        def numpy(self):
+            return self.a
+
+    def __init__(self, res):
+        self.A, self.chi2, self.S, self.Q = (self._T(x) for x in (res.A, res.chi2, res.S, res.Q))
+        self.logp = self._T(res.probability)
+        names = gc.AN_NAMES
+        ar = res.analyzer_results
+        idx = [ar[n].get('alpha_index', -1) if n in ar and not isinstance(ar[n], str) else -1 for n in names]
+        n_om = res.A.shape[-1]
+        Aout = [ar[n]['A_out'] if n in ar and not isinstance(ar[n], str) and 'A_out' in ar[n] else np.full(n_om, np.nan)
+                for n in names]
+        self.alpha_index, self.A_out = self._T(np.array(idx)), self._T(np.array(Aout))
+
+
+def _tau_maxent_from_fixture(g, **kw):
+    tm = mb.TauMaxEnt(cost_function=str(g["variant"]), probability='normal' if bool(g["use_probability"]) else None,
+                      reduce_singular_space=float(g["reduce_singular_space"]), **kw)
+    tm.set_verbosity(mb.VerbosityFlags.Quiet)
+    tm.set_G_tau_data(g["tau"], g["G"])
+    tm.omega = mb.DataOmegaMesh(g["omega"])
+    tm.alpha_mesh = mb.DataAlphaMesh(g["alpha_mesh"])
+    tm.set_error(float(g["err"]) if np.ndim(g["err"]) == 0 else g["err"])
+    return tm
+
+
+@pytest.mark.parametrize("name", ["g1_semicircular_prob.npz", "g2_synth_200x100.npz", "g3_plusminus_offdiag.npz",
+                                  "g4_bryan_200x100.npz", "g5_config1_cut1e-11.npz"])
+def test_tau_maxent_matches_reference_run(name):
+    """The same user script as oracle/make_golden.py ran on the reference, on this package."""
+    g = gc.load_golden(name)
+    tm = _tau_maxent_from_fixture(g)
+    res = tm.run()
+    assert len(tm.K.S) == int(g["ref_n_sv"])
+    np.testing.assert_allclose(res.alpha, g["ref_alpha"], rtol=1e-14)
+    np.testing.assert_allclose(tm.D.D, g["ref_D"], rtol=1e-13)
+    gc.check_against_reference(g, _ResView(res))
+    assert res.default_analyzer_name == 'LineFitAnalyzer'
+    np.testing.assert_array_equal(res.A_out, res.analyzer_results['LineFitAnalyzer']['A_out'])
+    np.testing.assert_allclose(res.H, res.A * tm.omega.delta[None, :], rtol=1e-15)
+    assert res.v.shape == (len(g["ref_alpha"]), int(g["ref_n_sv"]))
+    assert np.all(res.converged)
+
+
+def test_tau_maxent_vs_hand_assembled_loop():
+    """test/python/tau_maxent.py:31-135: TauMaxEnt and a MaxEntLoop assembled from its parts give the same
+    result field by field, and the probabilities are the reference's literal numbers to 6 decimals."""
+    g = gc.load_golden("g1_semicircular_prob.npz")
+    tm = mb.TauMaxEnt(probability='normal')
+    tm.set_verbosity(mb.VerbosityFlags.Quiet)
+    tm.set_G_tau_data(g["tau"], g["G"])
+    tm.alpha_mesh = mb.LogAlphaMesh(alpha_min=0.08, n_points=5)
+    tm.omega = mb.HyperbolicOmegaMesh(omega_min=-10, omega_max=10, n_points=200)
+    tm.set_error(1.e-3)
+    assert np.max(np.abs(mb.TauKernel(tm.tau, tm.omega).K - tm.K.K)) < 1.e-14
+    omega = mb.HyperbolicOmegaMesh(omega_min=-10, omega_max=10, n_points=200)
+    K = mb.TauKernel(tm.tau, omega)
+    D = mb.FlatDefaultModel(omega=omega)
+    Q = mb.MaxEntCostFunction(chi2=mb.NormalChi2(K=K, G=tm.G, err=1.e-3 * np.ones(len(tm.G))),
+                              S=mb.NormalEntropy(D=D), H_of_v=mb.NormalH_of_v(D=D, K=K))
+    log = mb.Logtaker()
+    log.verbose = mb.VerbosityFlags.Quiet
+    ml = mb.MaxEntLoop(cost_function=Q, minimizer=mb.LevenbergMinimizer(), logtaker=log,
+                       alpha_mesh=mb.LogAlphaMesh(alpha_min=0.08, n_points=5), probability='normal')
+    for a, b in ((ml.G, tm.G), (ml.alpha_mesh, tm.alpha_mesh), (ml.data_variable, tm.tau), (ml.err, tm.err),
+                 (ml.omega, tm.omega), (ml.D.D, tm.D.D), (ml.K.K, tm.K.K), (ml.K.S, tm.K.S)):
+        np.testing.assert_almost_equal(np.asarray(a), np.asarray(b), 13)
+    r1, r2 = ml.run(), tm.run()
+    assert np.max(np.abs(r1.A_out - r2.A_out)) < 1.e-14
+    for field in ('alpha', 'chi2', 'S', 'Q', 'A', 'H', 'v', 'probability', 'G', 'G_rec', 'omega'):
+        np.testing.assert_almost_equal(getattr(r1, field), getattr(r2, field), 13)
+    assert r1.matrix_structure is None and r2.effective_matrix_structure is None
+    for key in r1.analyzer_results:
+        np.testing.assert_almost_equal(r1.analyzer_results[key]['A_out'], r2.analyzer_results[key]['A_out'], 13)
+    assert sorted(r1.analyzer_results) == sorted(['LineFitAnalyzer', 'Chi2CurvatureAnalyzer', 'EntropyAnalyzer',
+                                                  'BryanAnalyzer', 'ClassicAnalyzer'])
+    np.testing.assert_almost_equal(r2.probability, [-8476.52812836, -2343.02752796, -704.28318351,
+                                                    -280.26627323, -175.30592555], 6)
+    # G_rec = K_delta A reproduces the data within the error bars at small alpha
+    assert np.max(np.abs(r2.G_rec[-1] - tm.G)) < 1e-2
+    # analyzer extras
+    lf = r2.analyzer_results['LineFitAnalyzer']
+    assert len(lf['linefit_params']) == 2 and len(lf['linefit_params'][0]) == 2 and 'linefit' in lf['info']
+    cv = r2.analyzer_results['Chi2CurvatureAnalyzer']['curvature']
+    assert cv.shape == (5,) and np.isnan(cv[0]) and np.isnan(cv[-1]) and not np.any(np.isnan(cv[1:-1]))
+    assert int(np.nanargmax(cv)) == r2.analyzer_results['Chi2CurvatureAnalyzer']['alpha_index']
+    dS = r2.analyzer_results['EntropyAnalyzer']['dS_dalpha']
+    ref = (r2.S[2:] - r2.S[:-2]) / (np.log(r2.alpha[2:]) - np.log(r2.alpha[:-2]))
+    np.testing.assert_allclose(dS[1:-1], ref, rtol=1e-12)
+    # pickling the array twin (test/python/pickle_maxent_result.py)
+    again = pickle.loads(pickle.dumps(r2.data))
+    np.testing.assert_array_equal(again.A_out, r2.A_out)
+    np.testing.assert_array_equal(again.chi2, r2.chi2)
+
+
+def test_elementwise_matches_reference_run():
+    """test/python/elementwise_maxent.py:101-188 on the reference's own fixture (G_tau_noise of
+    elementwise_g_tau.npz): elementwise, diagonal and hermiticity relations + the reference's numbers."""
+    g = gc.load_golden("g6_elementwise_2x2.npz")
+
+    def make(cls, **kw):
+        ew = cls(use_hermiticity=True, **kw)
+        ew.set_verbosity(mb.VerbosityFlags.Quiet)
+        ew.set_G_tau_data(g["tau"], g["G"])
+        ew.omega = mb.DataOmegaMesh(g["omega"])
+        ew.alpha_mesh = mb.DataAlphaMesh(g["alpha_mesh"])
+        ew.set_error(float(g["err"]))
+        return ew
+    ew = make(mb.ElementwiseMaxEnt)
+    res = ew.run()
+    assert res.matrix_structure == (2, 2) and res.chi2.shape == (2, 2, 8) and res.A.shape == (2, 2, 8, 80)
+    np.testing.assert_allclose(res.alpha, g["ref_alpha"], rtol=1e-14)
+    np.testing.assert_array_equal(res.A[1, 0], res.A[0, 1])           # hermiticity: exact copy
+    assert np.all(np.isnan(res.chi2[1, 0]))                           # (1,0) was not computed
+    for (i, j) in ((0, 0), (0, 1), (1, 1)):
+        assert res.analyzer_results[i][j]['LineFitAnalyzer']['alpha_index'] == int(g["ref_idx_LineFitAnalyzer_%d%d" % (i, j)])
+        np.testing.assert_allclose(res.chi2[i, j], g["ref_chi2"][i, j], rtol=1e-6)
+        scale = np.max(np.abs(g["ref_A"][i, j]), axis=-1, keepdims=True)
+        k = res.analyzer_results[i][j]['LineFitAnalyzer']['alpha_index']
+        assert np.max(np.abs(res.A[i, j, k] - g["ref_A"][i, j, k])) <= 1e-8 * scale[k]
+        assert np.max(np.abs(res.A[i, j, :k + 1] - g["ref_A"][i, j, :k + 1]) / scale[:k + 1]) < 1e-6
+    ref_out = g["ref_A_out"]
+    assert np.nanmax(np.abs(res.A_out - ref_out)) <= 1e-8 * np.nanmax(np.abs(ref_out))
+    # diagonal-only run gives the same diagonal elements (bitwise: same kernel, same launch shape per element)
+    dg = make(mb.DiagonalMaxEnt)
+    rd = dg.run()
+    for i in range(2):
+        np.testing.assert_array_equal(rd.A[i, i], res.A[i, i])
+    assert np.all(np.isnan(rd.A_out[0, 1]))
+    # element-at-a-time equals the batched pass
+    one = make(mb.ElementwiseMaxEnt)
+    r1 = one.run_element((1, 1))
+    np.testing.assert_array_equal(r1.A[1, 1], res.A[1, 1])
+    assert np.all(np.isnan(r1.A[0, 0]))
+    # norms of the diagonal spectra (test/python/elementwise_maxent.py:185-188: 2 decimals)
+    om = np.asarray(ew.omega)
+    for i in range(2):
+        assert abs(np.trapz(res.A_out[i, i], om) - 1.0) < 1e-2
+    assert abs(np.trapz(res.A_out[0, 1], om)) < 1e-2
+
+
+def test_poorman_runs_and_uses_diagonal_default_model():
+    """PoormanMaxEnt (python/elementwise_maxent.py:562-653): off-diagonal default model from the diagonal A_out."""
+    g = gc.load_golden("g6_elementwise_2x2.npz")
+    pm = mb.PoormanMaxEnt(use_hermiticity=True)
+    pm.set_verbosity(mb.VerbosityFlags.Quiet)
+    pm.set_G_tau_data(g["tau"], g["G"])
+    pm.omega = mb.DataOmegaMesh(g["omega"])
+    pm.alpha_mesh = mb.DataAlphaMesh(g["alpha_mesh"])
+    pm.set_error(float(g["err"]))
+    res = pm.run()
+    A00 = res.analyzer_results[0][0]['LineFitAnalyzer']['A_out']
+    A11 = res.analyzer_results[1][1]['LineFitAnalyzer']['A_out']
+    D = pm.maxent_offdiagonal.D.D
+    np.testing.assert_allclose(D, (np.sqrt(A00 * A11) + 1e-6) * pm.omega.delta, rtol=1e-13)
+    np.testing.assert_allclose(res.A[0, 0], g["ref_A"][0, 0], rtol=0, atol=1e-4 * np.max(g["ref_A"][0, 0]))
+    assert np.all(np.isfinite(res.A_out))
+    # large alpha: the off-diagonal H = D(e^x - e^-x) stays near zero
+    assert np.max(np.abs(res.A[0, 1, 0])) < np.max(np.abs(res.A[0, 1, -1])) + 1e-12
+
+
+def test_covariance_vs_error_vector():
+    """test/python/cov.py:53-90: a diagonal covariance matrix and the matching error vector describe the same
+    problem (the rotation only permutes / reorders the data space)."""
+    rng = np.random.RandomState(3)
+    g = gc.load_golden("g2_synth_200x100.npz")
+    err = 1e-4 * (1.0 + rng.rand(len(g["tau"])))
+
+    def base():
+        tm = mb.TauMaxEnt(reduce_singular_space=1e-11)
+        tm.set_verbosity(mb.VerbosityFlags.Quiet)
+        tm.set_G_tau_data(g["tau"], g["G"])
+        tm.omega = mb.DataOmegaMesh(g["omega"])
+        tm.alpha_mesh = mb.DataAlphaMesh(g["alpha_mesh"][:12])
+        return tm
+    t1 = base()
+    t1.set_error(err)
+    r1 = t1.run()
+    t2 = base()
+    t2.set_cov(np.diag(err ** 2))
+    assert t2.K._T is not None and t2.K.K.shape == (len(err), len(g["omega"]))
+    np.testing.assert_allclose(np.sort(t2.err), np.sort(err), rtol=1e-12)
+    r2 = t2.run()
+    np.testing.assert_allclose(r2.chi2, r1.chi2, rtol=1e-7)
+    assert np.max(np.abs(r2.A - r1.A)) < 1e-6 * np.max(np.abs(r1.A))
+    np.testing.assert_array_equal(r2.G_orig, g["G"])                   # the original data are kept
+    assert np.max(np.abs(r2.G_rec[-1] - g["G"])) < 5e-3               # G_rec lives in the original basis
+    # a dense covariance: whitening must reduce to the same chi2 definition r^T C^-1 r
+    C = np.diag(err ** 2) + 1e-9 * np.exp(-np.abs(np.subtract.outer(g["tau"], g["tau"])))
+    t3 = base()
+    t3.set_cov(C)
+    r3 = t3.run()
+    H = r3.H[3]
+    r = t3.K.K_delta @ r3.A[3] - g["G"]
+    np.testing.assert_allclose(r3.chi2[3], r @ np.linalg.solve(C, r), rtol=1e-6)
+    assert np.all(np.isfinite(H))
+    # switching back to a plain error undoes the rotation
+    t3.set_error(1e-4)
+    assert t3.K._T is None and t3.K.K.shape == (len(g["tau"]), len(g["omega"]))
+
+
+def test_threshold_skip_and_unsupported_combinations():
+    g = gc.load_golden("g2_synth_200x100.npz")
+    tm = _tau_maxent_from_fixture(g)
+    tm.set_G_tau_data(g["tau"], 1e-12 * g["G"])
+    tm.set_error(1e-4)
+    assert tm.run() is None and 'G below threshold' in tm.logtaker.get_error_messages()[0]
+    res = mb.MaxEntResult(matrix_structure=(1, 1))
+    assert tm.run(result=res, matrix_element=(0, 0)) is None and res.zero_elements == [(0, 0)]
+    tm2 = _tau_maxent_from_fixture(g)
+    tm2.cost_function.d_dv = True
+    with pytest.raises(NotImplementedError):
+        tm2.run()
+    tm3 = _tau_maxent_from_fixture(g)
+    tm3.scale_alpha = 'nonsense'
+    with pytest.raises(Exception):
+        tm3.run()
+    tm4 = _tau_maxent_from_fixture(g)
+    tm4.scale_alpha = 1.0
+    tm4.alpha_mesh = mb.DataAlphaMesh(g["ref_alpha"])                # already-scaled alphas with scale 1
+    r4 = tm4.run()
+    np.testing.assert_allclose(r4.chi2, g["ref_chi2"], rtol=1e-7)
+
+
+def test_alpha_loop_log_lines(capsys):
+    """The per-alpha report of python/maxent_loop.py:248-255, printed from the device counters."""
+    g = gc.load_golden("g2_synth_200x100.npz")
+    tm = _tau_maxent_from_fixture(g)
+    tm.set_verbosity(mb.VerbosityFlags.AlphaLoop | mb.VerbosityFlags.Timing)
+    tm.minimizer.maxiter = 5
+    res = tm.run()
+    out = capsys.readouterr().out.splitlines()
+    lines = [l for l in out if l.startswith("alpha[")]
+    assert len(lines) == len(res.alpha)
+    width = int(np.ceil(np.log10(len(res.alpha))))
+    assert lines[0].startswith("alpha[%*d] = %16.8e, chi2 = %16.8e, n_iter=" % (width, 0, res.alpha[0], res.chi2[0]))
+    assert any(l.endswith("!") for l in lines) and not np.all(res.converged)
+    assert any("did not converge" in l for l in out) and any(l.startswith("MaxEnt loop finished in") for l in out)
+    assert tm.minimizer.n_iter_last == int(res.n_iter[-1]) <= 5
