@@ -237,6 +237,7 @@ def run_native(a):
         k_ms.append(job.time_sweep_kernel(G_dev))
     kernel_ms = sum(k_ms) / len(k_ms)
     n_iter = int(res.n_iter.sum()); n_q = int(res.n_qeval.sum()); n_s = int(res.n_solve.sum())
+    n_trial = int(res.n_trial.sum()); n_batch = int(res.n_batch.sum())
     s = prob.n_sv
     flops = algorithmic_flops(n_iter, n_q, n_s, B * a.n_alpha, a.n_omega, s, False)
     flops_survey = flops + n_q * 2.0 * a.n_tau * s
@@ -289,6 +290,8 @@ def run_native(a):
                        "setup_s_once_per_kernel": round(setup_s, 3), "svd_sweeps": getattr(prob, "svd_sweeps", None),
                        "spectra_per_cta": prob.config["spectra_per_cta"], "smem_bytes": prob.config["smem_bytes"],
                        "lm_iterations_per_spectrum": n_iter / B, "q_evals_per_spectrum": n_q / B, "solves_per_spectrum": n_s / B,
+                       "device_trials_per_lm_iteration": n_trial / max(n_iter, 1),
+                       "device_batches_per_lm_iteration": n_batch / max(n_iter, 1),
                        "converged_frac": float((res.status & 1).double().mean()),
                        "linefit_idx_hist": {int(k): int(v) for k, v in zip(*np.unique(idx[:, 0], return_counts=True))},
                        "chi2curv_idx_hist": {int(k): int(v) for k, v in zip(*np.unique(idx[:, 1], return_counts=True))}},

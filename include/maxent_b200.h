@@ -97,6 +97,8 @@ typedef struct {
     int32_t* n_qeval;  /* [B, n_alpha]   cost-function evaluations (rounds) */
     int32_t* n_solve;  /* [B, n_alpha]   dense solves attempted */
     int32_t* status;   /* [B, n_alpha]   MX_STATUS_* bits */
+    int32_t* n_trial;  /* [B, n_alpha]   trial points the device evaluated (incl. mis-speculated ones); may be NULL */
+    int32_t* n_batch;  /* [B, n_alpha]   speculative batches (= passes over V' for cost evaluations); may be NULL */
 } MxSweepOut;
 
 /* Library / device info.  Returns the number of SMs of the current device (or <0). */

@@ -170,7 +170,7 @@ struct Ctl {
     int ufail[NROWS];
     int nb, nuniq;
     double jdmin;              // smallest |J_kk| (quick test for equivalent dampings)
-    int spec, ia, it, nq, ns, dir_up, cur_row, action, conv, last_len, ns_it0;
+    int spec, ia, it, nq, ns, dir_up, cur_row, action, conv, last_len, ns_it0, ntrial, nbatch;
     unsigned gchunk;           // chunks streamed so far (pipeline phase bookkeeping)
 };
 static_assert(sizeof(Ctl) <= 192 * sizeof(double), "Ctl must fit its reserved block");
@@ -859,7 +859,7 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
             sm[LY::o_tb + i] = (b == 0 && j < s) ? a.v0[j] : 0.0;
         }
         if (tid == 0) {
-            ctl.ia = 0; ctl.it = 0; ctl.nq = 0; ctl.ns = 0; ctl.dir_up = 1; ctl.last_len = 99;
+            ctl.ia = 0; ctl.it = 0; ctl.nq = 0; ctl.ns = 0; ctl.dir_up = 1; ctl.last_len = 99; ctl.ntrial = 1; ctl.nbatch = 1;
             ctl.alpha = a.alpha[0]; ctl.c0 = a.c0[sp];
             ctl.lm.mu = a.mu0; ctl.lm.Q0 = nan(""); ctl.lm.phase = PH_FIRST;
             ctl.nuniq = 1; ctl.nb = 0; ctl.urow[0] = 0; ctl.ufail[0] = 0;
@@ -907,6 +907,8 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                     if (a.o_niter) a.o_niter[o] = hit_max ? a.maxiter : ctl.it + 1;
                     if (a.o_nq) a.o_nq[o] = ctl.nq;
                     if (a.o_ns) a.o_ns[o] = ctl.ns;
+                    if (a.o_ntrial) a.o_ntrial[o] = ctl.ntrial;
+                    if (a.o_nbatch) a.o_nbatch[o] = ctl.nbatch;
                     if (a.o_status) a.o_status[o] = (!hit_max && ctl.conv) ? MX_STATUS_CONVERGED : 0;
                 }
                 if (a.o_v) for (int i = tid; i < s; i += NTHR) a.o_v[o * s + i] = sm[LY::o_v + i];
@@ -920,6 +922,7 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                     if (ctl.ia < a.n_alpha) {
                         ctl.alpha = a.alpha[ctl.ia];
                         ctl.lm.mu = a.mu0; ctl.lm.Q0 = nan(""); ctl.it = 0; ctl.nq = 1; ctl.ns = 0; ctl.dir_up = 1; ctl.last_len = 99;
+                        ctl.ntrial = 0; ctl.nbatch = 0;
                     }
                 }
                 __syncthreads();
@@ -1049,7 +1052,7 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                             ctl.urow[lane] = (carry_row >= 0 && lane >= carry_row) ? lane + 1 : lane;   // skip the carried row
                             ctl.ufail[lane] = 0;
                         }
-                        if (lane == 0) { ctl.nb = np; ctl.nuniq = npu; }
+                        if (lane == 0) { ctl.nb = np; ctl.nuniq = npu; ctl.ntrial += npu; ctl.nbatch += 1; }
                     }
                     if (lane == 0) { ctl.lm = L; ctl.ns = ns; ctl.nq = nq; ctl.conv = done; }
                 }

@@ -101,6 +101,12 @@ class SharedProblem(object):
             else:
                 M = (sqrtw[:, None] * (K @ V)).contiguous()
                 Q, Xi, P = self._svd(M, svd)
+            # The left vectors of singular values near the rounding floor come out of a one-sided Jacobi (or any
+            # SVD) with an orthogonality error ~ eps * S[0] / S[i]; chi2 = |Xi y - Q^T g|^2 + |(1 - Q Q^T) g|^2
+            # needs Q^T Q = 1.  Two Gram-Schmidt passes in order of decreasing singular value leave the
+            # well-determined columns untouched (to rounding) and move the others by an amount whose effect on
+            # K H is ~ 1e-2 * S[i] -- far below the data error.
+            Q = self._reorthonormalize(Q)
             self.P = P
             self.Vp = V if P is None else (V @ P).contiguous()
             self.Q = Q.contiguous()
@@ -126,6 +132,17 @@ class SharedProblem(object):
             _lib.check(self.lib.mx_layout_V(_ptr(self.Vp), self.n_omega, s, _ptr(self.Vt), stream), "mx_layout_V")
             self.engine = int(engine)
             self.config = _lib.sweep_config(s, self.engine)
+
+    @staticmethod
+    def _reorthonormalize(Q):
+        Q = Q.clone()
+        for j in range(Q.shape[1]):
+            q = Q[:, j]
+            if j:
+                for _ in range(2):
+                    q = q - Q[:, :j] @ (Q[:, :j].transpose(0, 1) @ q)
+            Q[:, j] = q / q.norm()
+        return Q
 
     def _svd(self, K, method):
         torch = _torch()
@@ -204,7 +221,7 @@ def svd_jacobi_host(K, device=None, max_sweeps=60):
 class SweepResult(object):
     """Device tensors produced by one call of the fused sweep (+ analyzers)."""
     __slots__ = ("alpha", "v", "A", "chi2", "S", "Q", "logp", "n_iter", "n_qeval", "n_solve", "status",
-                 "alpha_index", "A_out", "n_sv")
+                 "alpha_index", "A_out", "n_sv", "n_trial", "n_batch")
 
 
 def _stream(dev):
@@ -308,6 +325,8 @@ def run_sweep(prob, G, alpha_eff, probability=False, lm=None, chi2_factor=1.0, w
         r.n_qeval = torch.zeros((B, n_alpha), dtype=i32, device=dev)
         r.n_solve = torch.zeros((B, n_alpha), dtype=i32, device=dev)
         r.status = torch.zeros((B, n_alpha), dtype=i32, device=dev)
+        r.n_trial = torch.zeros((B, n_alpha), dtype=i32, device=dev)
+        r.n_batch = torch.zeros((B, n_alpha), dtype=i32, device=dev)
         ws_bytes = int(lib.mx_sweep_workspace_bytes(ctypes.byref(p), B))
         if ws_bytes < 0:
             _lib.check(ws_bytes, "mx_sweep_workspace_bytes")
@@ -315,7 +334,8 @@ def run_sweep(prob, G, alpha_eff, probability=False, lm=None, chi2_factor=1.0, w
         if ws is None or ws.numel() < ws_bytes:
             ws = prob._workspace = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         out = _lib.MxSweepOut(_ptr(r.v), _ptr(r.A), _ptr(r.chi2), _ptr(r.S), _ptr(r.Q), _ptr(r.logp),
-                              _ptr(r.n_iter), _ptr(r.n_qeval), _ptr(r.n_solve), _ptr(r.status))
+                              _ptr(r.n_iter), _ptr(r.n_qeval), _ptr(r.n_solve), _ptr(r.status),
+                              _ptr(r.n_trial), _ptr(r.n_batch))
         if time_kernel:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()

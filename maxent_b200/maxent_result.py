@@ -425,14 +425,16 @@ class MaxEntResult(MaxEntResultData):
         """Reconstructed data K_delta A for every alpha, in the original basis (python/maxent_result.py:905-908)."""
         return self._assemble('G_rec')
 
-    @saved
+    @property
     def n_iter(self):
-        """Levenberg iterations per alpha (device counter; not a field of the reference)."""
+        """Levenberg iterations per alpha (device counter; not a field of the reference, not saved)."""
         return self._assemble('n_iter')
 
-    @saved
+    @property
     def converged(self):
-        return self._assemble('converged')
+        """Per alpha: did the minimiser meet its convergence criterion (the '!' flag of the log lines)."""
+        c = self._assemble('converged')
+        return c.astype(bool) if not self._shape() else c
 
     def _per_element(self, values, default):
         shape = self._shape()

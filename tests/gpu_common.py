@@ -50,13 +50,19 @@ def rel_A(A, Aref):
     return np.max(np.abs(A - Aref), axis=-1) / np.max(np.abs(Aref), axis=-1)
 
 
-def check_against_reference(g, res, b=0):
-    """Tiers T2-T4 against the reference outputs stored in the fixture."""
+def check_against_reference(g, res, b=0, rtol_chi2_S=RTOL_WELL_DETERMINED):
+    """Tiers T2-T4 against the reference outputs stored in the fixture.  ``rtol_chi2_S`` is the floor for
+    chi2 and S separately (Q and A keep 1e-8): when the kernel matrix itself comes from another exp()
+    implementation (device TauKernel, 1 ulp) the Levenberg path may stop at a different point inside the
+    reference's own convergence ball (max|dQ/dv| < 1e-4); Q is stationary there (second-order error) but chi2
+    and S move at first order, in opposite directions."""
     A = res.A[b].cpu().numpy()
     chi2 = res.chi2[b].cpu().numpy()
     S = res.S[b].cpu().numpy()
     Q = res.Q[b].cpu().numpy()
     tolA, tolc, tolS = tolerances(g, "A"), tolerances(g, "chi2"), tolerances(g, "S")
+    tolQ = np.maximum(tolc, tolS)
+    tolc, tolS = np.maximum(tolc, rtol_chi2_S), np.maximum(tolS, rtol_chi2_S)
     dA = rel_A(A, g["ref_A"])
     assert np.all(dA <= tolA), "A: worst ratio %.2f at alpha idx %d" % (np.max(dA / tolA), int(np.argmax(dA / tolA)))
     dc = np.abs(chi2 / g["ref_chi2"] - 1)
@@ -64,7 +70,7 @@ def check_against_reference(g, res, b=0):
     dS = np.abs(S / g["ref_S"] - 1)
     assert np.all(dS <= np.maximum(tolS, tolA)), "S: %s" % (dS / np.maximum(tolS, tolA),)
     dQ = np.abs(Q / g["ref_Q"] - 1)
-    assert np.all(dQ <= np.maximum(tolc, tolS)), "Q: %s" % (dQ,)
+    assert np.all(dQ <= tolQ), "Q: %s" % (dQ,)
     if bool(g["use_probability"]):
         p = res.logp[b].cpu().numpy()
         ptol = np.maximum(PROB_RTOL, NOISE_FACTOR * running_max(g["noise_chi2"]))
