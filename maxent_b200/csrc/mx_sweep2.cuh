@@ -332,6 +332,146 @@ __device__ __forceinline__ void chol_solve(const double (&A)[Lay<NT>::NTRI][2], 
 }
 
 // ------------------------------------------------------------------------------------------
+// "lean" blocked Cholesky (NT <= 7): left-looking, at most 10 strictly-lower tiles of L stay in registers, the
+// leading block columns are parked in a per-warp slice of shared memory, the diagonal tiles are dropped once
+// their inverse U is known.  ~100 registers per thread instead of ~210, so ALL eight warps of the CTA can
+// factorise at the same time (eight damping trials per round) without borrowing registers via setmaxnreg.
+// ------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int lean_nsm(int NT) {
+    int nsm = 0;
+    while (nsm < NT && (NT - 1 - nsm) * (NT - nsm) / 2 > 10) ++nsm;
+    return nsm;
+}
+template <int NT>
+struct Lean {
+    static constexpr int NSM = lean_nsm(NT);                                   // block columns kept in shared memory
+    static constexpr int NREG = (NT - 1 - NSM) * (NT - NSM) / 2;               // strictly-lower tiles kept in registers
+    static constexpr int NSMT = NT * (NT - 1) / 2 - NREG;                      // tiles per warp in shared memory
+    static constexpr int RDIM = NREG > 0 ? NREG : 1;
+    __host__ __device__ static constexpr int before(int J, int from) {
+        int o = 0;
+        for (int j = from; j < J; ++j) o += NT - 1 - j;
+        return o;
+    }
+    __host__ __device__ static constexpr int sidx(int I, int J) { return before(J, 0) + I - J - 1; }
+    __host__ __device__ static constexpr int ridx(int I, int J) { return J >= NSM ? before(J, NSM) + I - J - 1 : 0; }
+};
+
+// strictly-lower tile (I, J) of the factor: shared memory for the leading columns, registers for the rest
+template <int NT>
+__device__ __forceinline__ double2 lean_tile(const double* __restrict__ Lsm, const double (&R)[Lean<NT>::RDIM][2], int I, int J,
+                                             int lane) {
+    if (J < Lean<NT>::NSM) return *reinterpret_cast<const double2*>(Lsm + Lean<NT>::sidx(I, J) * 64 + 2 * lane);
+    return make_double2(R[Lean<NT>::ridx(I, J)][0], R[Lean<NT>::ridx(I, J)][1]);
+}
+
+// block column JB: C[I] = in(I, JB) - sum_{K<JB} L[I][K] L[JB][K]^T, Cholesky of the diagonal tile together with an
+// identity tile (-> U = L_d^{-T}), L[I][JB] = C[I] U for the tiles below (same arithmetic as chol_panel above)
+template <int NT, int JB, class Load>
+__device__ __forceinline__ void lean_steps(Load& load, double* __restrict__ Lsm, double (&R)[Lean<NT>::RDIM][2], double (&U)[NT][2],
+                                           bool& ok, double& logdet, bool want_logdet, int r, int q, int lane) {
+    if constexpr (JB < NT) {
+        constexpr int NC = NT - JB;
+        double C[NC][2];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) { const double2 t = load(JB + i, JB); C[i][0] = t.x; C[i][1] = t.y; }
+#pragma unroll
+        for (int K = 0; K < JB; ++K) {
+            const double2 y = lean_tile<NT>(Lsm, R, JB, K, lane);
+            mma_nt(C[0], -y.x, -y.y, y.x, y.y);
+#pragma unroll
+            for (int i = 1; i < NC; ++i) {
+                const double2 x = lean_tile<NT>(Lsm, R, JB + i, K, lane);
+                mma_nt(C[i], -x.x, -x.y, y.x, y.y);
+            }
+        }
+        double E[2];
+        E[0] = (r == 2 * q) ? 1.0 : 0.0;
+        E[1] = (r == 2 * q + 1) ? 1.0 : 0.0;
+        double(&P0)[2] = C[0];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int jq = j >> 1, je = j & 1;
+            const double ajj = shfl(P0[je], 4 * j + jq);
+            const double lk0 = shfl(P0[je], 8 * q + jq);              // a[2q][j]
+            const double lk1 = shfl(P0[je], 8 * q + 4 + jq);          // a[2q+1][j]
+            const int src = (lane & ~3) | jq;
+            const double lp = shfl(P0[je], src);                      // a[r][j]
+            const double le = shfl(E[je], src);
+            if (!(ajj > 0.0)) ok = false;
+            if (want_logdet) logdet += log(ajj);
+            const double inv = rcp_nr(ajj);
+            const double rinv = rsqrt_nr(ajj);
+            const double p0 = lp * lk0, p1 = lp * lk1, e0 = le * lk0, e1 = le * lk1;
+            if (2 * q > j) { P0[0] = fma(-p0, inv, P0[0]); E[0] = fma(-e0, inv, E[0]); }
+            if (2 * q + 1 > j) { P0[1] = fma(-p1, inv, P0[1]); E[1] = fma(-e1, inv, E[1]); }
+            if (q == jq) { P0[je] *= rinv; E[je] *= rinv; }          // final values of column j
+        }
+        U[JB][0] = E[0];
+        U[JB][1] = E[1];
+        if constexpr (NC > 1) {
+            // W[r][2q+e] = U[2q+e][r], which lives in lane (2q+e, r/2), register r%2
+            const int s0 = 8 * q + (r >> 1), s1 = s0 + 4;
+            const double a0 = shfl(E[0], s0), b0 = shfl(E[1], s0);
+            const double a1 = shfl(E[0], s1), b1 = shfl(E[1], s1);
+            const double W0 = (r & 1) ? b0 : a0, W1 = (r & 1) ? b1 : a1;
+#pragma unroll
+            for (int i = 1; i < NC; ++i) {
+                double c[2] = {0.0, 0.0};
+                mma_nt(c, C[i][0], C[i][1], W0, W1);
+                if constexpr (JB < Lean<NT>::NSM) {
+                    *reinterpret_cast<double2*>(Lsm + Lean<NT>::sidx(JB + i, JB) * 64 + 2 * lane) = make_double2(c[0], c[1]);
+                } else {
+                    R[Lean<NT>::ridx(JB + i, JB)][0] = c[0];
+                    R[Lean<NT>::ridx(JB + i, JB)][1] = c[1];
+                }
+            }
+        }
+        lean_steps<NT, JB + 1>(load, Lsm, R, U, ok, logdet, want_logdet, r, q, lane);
+    }
+}
+
+// Solve L L^T x = rhs with the lean factor (same scheme as chol_solve)
+template <int NT>
+__device__ __forceinline__ void lean_solve(const double* __restrict__ Lsm, const double (&R)[Lean<NT>::RDIM][2],
+                                           const double (&U)[NT][2], const double* __restrict__ rhs, double (&xr)[NT], int r,
+                                           int q, int lane, double* __restrict__ zscr) {
+    {
+        double zc[NT][2];
+#pragma unroll
+        for (int jb = 0; jb < NT; ++jb) {
+            double acc = 0.0;
+#pragma unroll
+            for (int J = 0; J < jb; ++J) {
+                const double2 t = lean_tile<NT>(Lsm, R, jb, J, lane);
+                acc = fma(t.x, zc[J][0], fma(t.y, zc[J][1], acc));
+            }
+            double rr = rhs[8 * jb + r];
+            if (jb > 0) rr -= quadreduce(acc);
+            zc[jb][0] = colreduce(U[jb][0] * rr);
+            zc[jb][1] = colreduce(U[jb][1] * rr);
+            if (r == 0) *reinterpret_cast<double2*>(zscr + 8 * jb + 2 * q) = make_double2(zc[jb][0], zc[jb][1]);
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int jb = NT - 1; jb >= 0; --jb) {
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int I = jb + 1; I < NT; ++I) {
+            const double2 t = lean_tile<NT>(Lsm, R, I, jb, lane);
+            c0 = fma(t.x, xr[I], c0);
+            c1 = fma(t.y, xr[I], c1);
+        }
+        const double2 z = *reinterpret_cast<const double2*>(zscr + 8 * jb + 2 * q);
+        double z0 = z.x, z1 = z.y;
+        if (jb < NT - 1) { z0 -= colreduce(c0); z1 -= colreduce(c1); }
+        xr[jb] = quadreduce(fma(U[jb][0], z0, U[jb][1] * z1));
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
 // H-pass tile ownership: rows of the lower triangle owned by tile-half 0 (the rest belongs to half 1)
 // ------------------------------------------------------------------------------------------
 __host__ __device__ constexpr unsigned rowmask0(int NT) {
@@ -501,9 +641,15 @@ __device__ __forceinline__ void hpass_body(const Pipe<NT>& pipe, unsigned g0, co
 template <int NT>
 __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const SweepArgs a) {
     using LY = Lay<NT>;
-    // NT <= 8: two CTAs per SM at 128 registers per thread, the solver warp group is lent registers for the
-    // Cholesky phase; NT > 8: one CTA per SM (shared memory), every thread owns 255 registers all the time
-    constexpr bool REGSPLIT = NT <= 8;
+    // NT <= 7: two CTAs per SM at 128 registers per thread, all eight warps factorise with the lean Cholesky;
+    // NT == 8: two CTAs per SM, four solver warps are lent the other warp group's registers (setmaxnreg) for the
+    // register-resident Cholesky; NT > 8: one CTA per SM (shared memory), every thread owns 255 registers
+    constexpr bool LEAN = NT <= 7;
+    constexpr bool REGSPLIT = NT == 8;
+    using LN = Lean<NT>;
+    static_assert(!LEAN || NT * NT * 64 + 5 * LN::NSMT * 64 <= NSTAGE * LY::STAGE_D,
+                  "the parked tiles of warps 0-4 must not overlap Zfull (warp 0 factorises while Zfull is live)");
+    static_assert(!LEAN || NWARP * LN::NSMT * 64 <= NSTAGE * LY::STAGE_D, "parked tiles must fit in the staging area");
     constexpr int SP = LY::SP;
     constexpr int NTRI = LY::NTRI;
     extern __shared__ __align__(128) double sm[];
@@ -771,6 +917,45 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
     // ---- P3: factorise J + shift(mu_u) and solve for every unique trial (one solver warp per matrix) -------
     auto solve_trials = [&]() {
         const int nuniq = ctl.nuniq;
+        if constexpr (LEAN) {
+            // every warp factorises one shifted Hessian: eight trials per round
+            double* const Lsm = sm + LY::o_stage + NSTAGE * LY::STAGE_D - (warp + 1) * LN::NSMT * 64;
+            for (int u = warp; u < nuniq; u += NWARP) {
+                const double mu = ctl.umu[u];
+                auto load = [&](int I, int J) -> double2 {
+                    double2 v = *reinterpret_cast<const double2*>(sm + LY::o_J + tri(I, J) * 64 + 2 * lane);
+                    if (I == J) {
+                        const int i0 = 8 * I + r;
+                        if (i0 < s) {
+                            const double sh = shift_of(i0, mu);
+                            if (r == 2 * q) v.x += sh;
+                            if (r == 2 * q + 1) v.y += sh;
+                        }
+                    }
+                    return v;
+                };
+                double R[LN::RDIM][2];
+                double U[NT][2];
+                bool ok = true;
+                double ld = 0.0;
+                lean_steps<NT, 0>(load, Lsm, R, U, ok, ld, false, r, q, lane);
+                ok = __all_sync(0xffffffffu, ok);
+                double xr[NT];
+                lean_solve<NT>(Lsm, R, U, sm + LY::o_rhs, xr, r, q, lane, sm + LY::o_dvb + u * SP);
+                if (q == 0) {
+#pragma unroll
+                    for (int I = 0; I < NT; ++I) {
+                        const int i0 = 8 * I + r;
+                        const double dv = ok ? xr[I] : 0.0;
+                        sm[LY::o_dvb + u * SP + i0] = dv;
+                        sm[LY::o_tb + u * SP + i0] = ok ? sm[LY::o_v + i0] - dv : 0.0;
+                    }
+                }
+                if (lane == 0) ctl.ufail[u] = ok ? 0 : 1;
+            }
+            __syncthreads();
+            return;
+        }
         regs_to_solvers();
         if (warp < NSOLVE) {
             for (int u = warp; u < nuniq; u += NSOLVE) {
@@ -815,27 +1000,37 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
     // ---- log det(I + eta Xi Z Xi / alpha) by warp 0 (probabilities.py:76-85 via Sylvester) -----------------
     auto logdet_prob = [&]() -> double {       // warp 0 only; returns NaN on a failed factorisation
         const double* Zf = sm + LY::o_stage;
-        double A[NTRI][2];
-#pragma unroll
-        for (int I = 0; I < NT; ++I) {
-#pragma unroll
-            for (int J = 0; J <= I; ++J) {
-                const double2 z = *reinterpret_cast<const double2*>(Zf + (I * NT + J) * 64 + 2 * lane);
-                const int i0 = 8 * I + r, j0 = 8 * J + 2 * q;
-                const double xi_i = sm[LY::o_xi + i0];
-                double m0 = a.eta * xi_i * z.x * sm[LY::o_xi + j0] / ctl.alpha;
-                double m1 = a.eta * xi_i * z.y * sm[LY::o_xi + j0 + 1] / ctl.alpha;
-                if (i0 >= s || j0 >= s) m0 = 0.0;
-                if (i0 >= s || j0 + 1 >= s) m1 = 0.0;
-                if (i0 == j0) m0 += 1.0;
-                if (i0 == j0 + 1) m1 += 1.0;
-                A[tri(I, J)][0] = m0; A[tri(I, J)][1] = m1;
-            }
-        }
+        auto entry = [&](int I, int J) -> double2 {
+            const double2 z = *reinterpret_cast<const double2*>(Zf + (I * NT + J) * 64 + 2 * lane);
+            const int i0 = 8 * I + r, j0 = 8 * J + 2 * q;
+            const double xi_i = sm[LY::o_xi + i0];
+            double m0 = a.eta * xi_i * z.x * sm[LY::o_xi + j0] / ctl.alpha;
+            double m1 = a.eta * xi_i * z.y * sm[LY::o_xi + j0 + 1] / ctl.alpha;
+            if (i0 >= s || j0 >= s) m0 = 0.0;
+            if (i0 >= s || j0 + 1 >= s) m1 = 0.0;
+            if (i0 == j0) m0 += 1.0;
+            if (i0 == j0 + 1) m1 += 1.0;
+            return make_double2(m0, m1);
+        };
         double U[NT][2];
         bool ok = true;
         double ld = 0.0;
-        chol_steps<NT, 0>(A, U, ok, ld, true, r, q, lane);
+        if constexpr (LEAN) {
+            double* const Lsm = sm + LY::o_stage + NSTAGE * LY::STAGE_D - LN::NSMT * 64;     // warp 0's slice, beyond Zfull
+            double R[LN::RDIM][2];
+            lean_steps<NT, 0>(entry, Lsm, R, U, ok, ld, true, r, q, lane);
+        } else {
+            double A[NTRI][2];
+#pragma unroll
+            for (int I = 0; I < NT; ++I) {
+#pragma unroll
+                for (int J = 0; J <= I; ++J) {
+                    const double2 m = entry(I, J);
+                    A[tri(I, J)][0] = m.x; A[tri(I, J)][1] = m.y;
+                }
+            }
+            chol_steps<NT, 0>(A, U, ok, ld, true, r, q, lane);
+        }
         ok = __all_sync(0xffffffffu, ok);
         return ok ? ld : nan("");
     };
@@ -1006,18 +1201,24 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                             if (lane == 0) ctl.urow[ID_CARRY] = -1;
                         }
                         __syncwarp();
-                        // plan: continue a copy of the machine with pretended outcomes to list the next dampings.
-                        // Width: four unique trials (one solver round) when the previous iteration was short and
-                        // this is the first batch of the iteration, else eight.
-                        LM P = L;
+                        // plan: continue copies of the machine with pretended outcomes to list the next dampings.
+                        // While the direction of this iteration's walk is not known yet (no probe outcome), BOTH
+                        // branches are planned: the downward walk gets most of the budget (78 % of the iterations of
+                        // the benchmark spectra walk down, 98 % of those that follow an upward one; tools/lm_trace.py),
+                        // the upward walk the rest.  A pump (Q rises: mu *= nu until it does not) continues on the
+                        // upward grid, so it is planned upward at full width.
                         int np = 0, npu = 0;
-                        const int maxu = (ns == ctl.ns_it0 && ctl.last_len <= 4 && L.phase == PH_FIRST) ? 4 : MAXB;
-                        const bool dir_up = ctl.dir_up != 0;
+                        int budget = MAXB;
+                        bool dir = true;
+                        const bool undecided = (L.phase == PH_FIRST || L.phase == PH_PROBE);
+                        if (undecided) { dir = false; budget = ctl.dir_up ? MAXB - 1 : MAXB - 2; }
+                        else if (L.phase == PH_WALK) dir = (L.nuf == a.nu);
+                        LM P = L;
                         const bool have_carry = carry_row >= 0;
                         const double cmu = shfl(u_mu, ID_CARRY), cQ = shfl(u_Q, ID_CARRY);
                         double p_mu = 0.0, pu_mu = 0.0, pu_q = 0.0;       // planned table entry / unique trial of this lane
                         int p_slot = 0;
-                        auto look_plan = [&](double mu, int kind, double Qref, double& Q, int& id) -> bool {
+                        auto find_or_add = [&](double mu, int kind, double Qref, double& Q, int& id) -> bool {
                             if (have_carry && maybe(mu, cmu) && equiv_full(mu, cmu)) { Q = cQ; id = ID_CARRY; return true; }
                             const unsigned m = __ballot_sync(0xffffffffu, lane < np && p_mu == mu);
                             if (m) {
@@ -1035,17 +1236,32 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                                     return true;
                                 }
                             }
-                            if (npu == maxu || np == NTAB) return false;
+                            if (npu >= budget || np == NTAB) return false;
                             double pv;
                             if (kind == 0) pv = isnan(Qref) ? 0.0 : Qref;                        // first trial / pump: "accepted"
-                            else if (kind == 1) pv = dir_up ? Qref - (1.0 + fabs(Qref)) : Qref + (1.0 + fabs(Qref));
                             else pv = Qref - (1.0 + fabs(Qref));                                  // walk: "still improving"
                             if (lane == np) { p_mu = mu; p_slot = npu; }
                             if (lane == npu) { pu_mu = mu; pu_q = pv; }
                             id = 100 + npu; Q = pv; ++np; ++npu;
                             return true;
                         };
+                        auto look_plan = [&](double mu, int kind, double Qref, double& Q, int& id) -> bool {
+                            if (!find_or_add(mu, kind, Qref, Q, id)) return false;
+                            if (kind == 1) {
+                                // the probe decides the direction: steer this run; a probe that IS the current candidate
+                                // (bitwise the same shifted matrix) gives Q2 == Q1, i.e. "not lower"
+                                if (id == P.dv) Q = Qref;
+                                else Q = dir ? Qref - (1.0 + fabs(Qref)) : Qref + (1.0 + fabs(Qref));
+                            }
+                            return true;
+                        };
                         lm_run(P, a.nu, a.max_mu, eps_nu, look_plan);
+                        if (undecided && npu < MAXB) {         // the other branch with what is left of the batch
+                            P = L;
+                            dir = true;
+                            budget = MAXB;
+                            lm_run(P, a.nu, a.max_mu, eps_nu, look_plan);
+                        }
                         if (lane < np) { ctl.bmu[lane] = p_mu; ctl.bslot[lane] = p_slot; }
                         if (lane < npu) {
                             ctl.umu[lane] = pu_mu;
@@ -1060,7 +1276,18 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                 if (ctl.conv) break;
                 for (int i = tid; i < MAXB * SP; i += NTHR) if (i >= ctl.nuniq * SP) sm[LY::o_tb + i] = 0.0;
                 solve_trials();
-                tpass();
+                {
+                    // every factorisation of the batch failed (J + mu not positive definite numerically, the early
+                    // part of a pump): all Q are NaN by definition, no pass over V' is needed
+                    bool allfail = true;
+                    for (int u = 0; u < ctl.nuniq; ++u) allfail = allfail && (ctl.ufail[u] != 0);
+                    if (allfail) {
+                        if (tid < ctl.nuniq) { ctl.uQ[tid] = nan(""); ctl.uchi2[tid] = nan(""); ctl.uS[tid] = nan(""); }
+                        __syncthreads();
+                    } else {
+                        tpass();
+                    }
+                }
             }
             // ---- accept: v -= dv ; the accepted trial becomes the current point (levenberg_minimizer.py:239-243) ----
             {
