@@ -1255,12 +1255,55 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                             }
                             return true;
                         };
-                        lm_run(P, a.nu, a.max_mu, eps_nu, look_plan);
-                        if (undecided && npu < MAXB) {         // the other branch with what is left of the batch
-                            P = L;
-                            dir = true;
-                            budget = MAXB;
+                        // Fast paths for the three common situations: the dampings the machine would visit are written
+                        // down directly, with the machine's own arithmetic (mu * nu, mu / (1/nu), mu * (1/nu), ...), instead
+                        // of running it on pretended outcomes.  The plan is only a proposal -- the replay above decides
+                        // everything on real values and re-plans when an entry is missing -- so a fast path can cost
+                        // speculation efficiency but never change a result.
+                        bool fast = false;
+                        if (!bryan) {
+                            const double nu = a.nu, inu = 1.0 / a.nu;
+                            auto add_unique = [&](double mu) {
+                                if (lane == np) { p_mu = mu; p_slot = npu; }
+                                if (lane == npu) { pu_mu = mu; pu_q = 0.0; }
+                                ++np; ++npu;
+                            };
+                            if (L.phase == PH_PUMP && !have_carry && !maybe(L.mu * nu, L.mu)) {
+                                double m = L.mu;                       // pump: mu *= nu until Q stops rising (:203-206)
+                                for (int k = 0; k < MAXB; ++k) { m = m * nu; add_unique(m); }
+                                fast = true;
+                            } else if (L.phase == PH_WALK && have_carry && cmu == L.mu && !maybe(L.mu * L.nuf, L.mu)) {
+                                double m = L.mu;                       // walk: mu *= nuf while Q improves (:226-233)
+                                for (int k = 0; k < MAXB; ++k) { m = m * L.nuf; add_unique(m); }
+                                fast = true;
+                            } else if (L.phase == PH_FIRST && !have_carry && L.mu > 64.0 * eps_nu && L.mu < a.max_mu / 64.0 &&
+                                       !maybe(L.mu * nu, L.mu)) {
+                                const double m0 = L.mu, m1 = nu * m0;
+                                add_unique(m0);                        // dv = solve(J + mu)            (:192)
+                                add_unique(m1);                        // dv2 = solve(J + nu * mu)      (:209)
+                                const int ndown = ctl.dir_up ? MAXB - 3 : MAXB - 4;
+                                double m = m0 / inu;                   // probe lost: mu /= nuf, nuf = 1/nu   (:221-224)
+                                for (int k = 0; k <= ndown; ++k) {
+                                    m = m * inu;
+                                    if (k == 0) {                      // first walk point = mu again, up to rounding
+                                        if (m == m0) continue;
+                                        if (equiv_full(m, m0)) { if (lane == np) { p_mu = m; p_slot = 0; } ++np; continue; }
+                                    }
+                                    if (npu < MAXB) add_unique(m);
+                                }
+                                m = m0 * nu;                           // probe won: mu *= nu, walk upward   (:214-218)
+                                while (npu < MAXB) { m = m * nu; add_unique(m); }
+                                fast = true;
+                            }
+                        }
+                        if (!fast) {
                             lm_run(P, a.nu, a.max_mu, eps_nu, look_plan);
+                            if (undecided && npu < MAXB) {         // the other branch with what is left of the batch
+                                P = L;
+                                dir = true;
+                                budget = MAXB;
+                                lm_run(P, a.nu, a.max_mu, eps_nu, look_plan);
+                            }
                         }
                         if (lane < np) { ctl.bmu[lane] = p_mu; ctl.bslot[lane] = p_slot; }
                         if (lane < npu) {
