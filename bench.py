@@ -31,6 +31,8 @@ UNIT = "spectra/s"
 # Measured FP64 peak of this pool's B200 (tools/fp64_microbench.cu -> profiles/r01_fp64_microbench.json,
 # DMMA m8n8k4 and DFMA both saturate at 37.0 TFLOP/s).  MEASURED_PEAKS.json holds no FP64 figure.
 FP64_PEAK_FALLBACK_TFLOPS = 37.0
+# DRAM traffic of the sweep kernel from the ncu capture under profiles/ (bytes read + written, per spectrum)
+NCU_DRAM_BYTES_PER_SPECTRUM = int((13.916928e6 + 4.816254e9) / 296)   # profiles/r01b_sweep2_ncu_full_summary.json
 
 
 def parse_args():
@@ -266,14 +268,20 @@ def run_native(a):
     h2d, d2h = out.h2d_bytes, out.d2h_bytes
 
     # ---- max over ranks -------------------------------------------------------------------------------
-    t = torch.tensor([dev_ms, e2e_ms, kernel_ms], dtype=torch.float64, device=dev)
+    gather_ms = 0.0
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        # the one collective of the job: gather the analyzer outputs on rank 0 (NCCL over NVLink)
+        # the one collective of the job: gather the analyzer outputs on rank 0 (NCCL over NVLink), once per job
+        barrier()
+        t_g = time.time()
         gathered = batched.gather_results(out, dst=0)
+        barrier()
+        gather_ms = (time.time() - t_g) * 1e3
         if rank == 0:
             assert gathered["alpha_index"].shape[0] == world * B
-    dev_ms, e2e_ms, kernel_ms_max = [float(x) for x in t.tolist()]
+    t = torch.tensor([dev_ms, e2e_ms, kernel_ms, gather_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, kernel_ms_max, gather_ms = [float(x) for x in t.tolist()]
 
     if rank == 0:
         total = world * B * a.steps
@@ -287,6 +295,7 @@ def run_native(a):
             "config": {"workload": workload_name(a), "n_sv": s, "parallelism": "spectra sharded x%d, no data-path collective" % world,
                        "l2": "inputs/outputs larger than L2 (G %.0f MB, A(alpha) %.1f GB per step); V' (%.0f KB) is L2-resident by design"
                              % (B * a.n_tau * 8 / 1e6, B * a.n_alpha * a.n_omega * 8 / 1e9, prob.Vt.numel() * 8 / 1e3),
+                       "final_gather_ms_once_per_job": round(gather_ms, 3),
                        "setup_s_once_per_kernel": round(setup_s, 3), "svd_sweeps": getattr(prob, "svd_sweeps", None),
                        "spectra_per_cta": prob.config["spectra_per_cta"], "smem_bytes": prob.config["smem_bytes"],
                        "lm_iterations_per_spectrum": n_iter / B, "q_evals_per_spectrum": n_q / B, "solves_per_spectrum": n_s / B,
@@ -300,7 +309,11 @@ def run_native(a):
             "gpu_launches": a.steps * job.launches_per_step,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "mx::sweep_kernel", "kernel_ms": kernel_ms,
+                         "traffic": NCU_DRAM_BYTES_PER_SPECTRUM * B, "traffic_unit": "bytes per launch",
+                         "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one 296-spectrum "
+                                           "launch (profiles/), scaled to this launch's spectra; algorithmic bytes per spectrum = "
+                                           "G in + A(alpha) out = %d" % (a.n_tau * 8 + a.n_alpha * a.n_omega * 8),
+                         "kernel": "mx2::sweep2_kernel", "kernel_ms": kernel_ms,
                          "kernel_share_of_step": kernel_ms / (dev_ms / a.steps),
                          "flops_per_launch": flops, "flops_per_spectrum": flops / B,
                          "flops_survey_formula_per_spectrum": flops_survey / B,

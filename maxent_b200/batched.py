@@ -266,11 +266,14 @@ def gather_results(out, dst=0):
     world, rank = dist.get_world_size(), dist.get_rank()
     backend = dist.get_backend()
     got = {}
+    dev_res = getattr(out, "device", None)
     for name in ("alpha_index", "chi2", "A_out"):
-        arr = getattr(out, name)
-        t = torch.as_tensor(np.ascontiguousarray(arr))
-        if backend == "nccl":
-            t = t.cuda()
+        if backend == "nccl" and dev_res is not None and getattr(dev_res, name, None) is not None:
+            t = getattr(dev_res, name).contiguous()          # results are still resident: no host round trip
+        else:
+            t = torch.as_tensor(np.ascontiguousarray(getattr(out, name)))
+            if backend == "nccl":
+                t = t.cuda()
         sizes = [torch.zeros(1, dtype=torch.int64, device=t.device) for _ in range(world)]
         dist.all_gather(sizes, torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device))
         if rank == dst:

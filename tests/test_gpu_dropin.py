@@ -271,3 +271,34 @@ def test_alpha_loop_log_lines(capsys):
     assert any(l.endswith("!") for l in lines) and not np.all(res.converged)
     assert any("did not converge" in l for l in out) and any(l.startswith("MaxEnt loop finished in") for l in out)
     assert tm.minimizer.n_iter_last == int(res.n_iter[-1]) <= 5
+
+
+def test_config4_large_kernel_full_probability_analysis():
+    """BASELINE config 4: n_tau = 10000, n_omega = 2000, 100 alphas, probability + Bryan/Classic analysis, through
+    TauMaxEnt.  The reference's own run of this case (205 s + 298 s setup on 8 cores, BASELINE.md / SURVEY.md 6)
+    gave n_sv = 54 and the analyzer picks LineFit 38, Chi2Curvature 48, Entropy 92, Classic 99."""
+    from oracle import maxent_oracle as mo
+    pr = mo.synthetic_problem(10000, 2000, mu=1.0, seed=1234)
+    tm = mb.TauMaxEnt(probability='normal', reduce_singular_space=1e-11)
+    tm.set_verbosity(mb.VerbosityFlags.Quiet)
+    tm.set_G_tau_data(pr["tau"], pr["G"][0])
+    tm.omega = mb.HyperbolicOmegaMesh(-10, 10, 2000)
+    tm.alpha_mesh = mb.LogAlphaMesh(0.01, 2000, 100)
+    tm.set_error(1e-4)
+    res = tm.run()
+    assert len(tm.K.S) == 54
+    picks = {k: res.analyzer_results[k]['alpha_index'] for k in
+             ('LineFitAnalyzer', 'Chi2CurvatureAnalyzer', 'EntropyAnalyzer', 'ClassicAnalyzer')}
+    assert picks == {'LineFitAnalyzer': 38, 'Chi2CurvatureAnalyzer': 48, 'EntropyAnalyzer': 92, 'ClassicAnalyzer': 99}
+    assert np.all(res.converged) and np.all(np.isfinite(res.probability))
+    assert np.all(np.diff(res.probability) > 0)                     # p still rising at the smallest alpha (BASELINE.md)
+    # chi2 and S reported by the device equal the values recomputed from A with the full kernel matrix
+    H = res.H[[0, 38, 48, 99]]
+    r = (H @ pr["K"].T - pr["G"][0][None, :]) / 1e-4
+    np.testing.assert_allclose((r * r).sum(1), res.chi2[[0, 38, 48, 99]], rtol=1e-8)
+    D = tm.D.D
+    np.testing.assert_allclose((H - D - H * np.log(H / D)).sum(1), res.S[[0, 38, 48, 99]], rtol=1e-9)
+    # Bryan's average is a convex combination of the A_alpha
+    br = res.analyzer_results['BryanAnalyzer']['A_out']
+    assert np.all(br >= res.A.min(0) - 1e-12) and np.all(br <= res.A.max(0) + 1e-12)
+    assert abs(np.trapezoid(res.A_out, np.asarray(tm.omega)) - 1.0) < 1e-3
