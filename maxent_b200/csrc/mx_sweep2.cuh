@@ -73,6 +73,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// L2 policy for the per-CTA scratch rows (w = dH/dx of the evaluated trials): they are rewritten every batch and read
+// back by the H-pass, so they should stay in L2 while the A(alpha) output streams through (written once, never read)
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void st_keep_v2(double* p, double x, double y, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(x), "d"(y), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
@@ -685,6 +695,7 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
     __syncthreads();
 
     const Pipe<NT> pipe{sm + LY::o_stage, a.Vt, bar_full, bar_empty, tid, lane, n_kt, nch};
+    const uint64_t keep_pol = l2_evict_last_policy();
 
     // Register hand-over around a solver phase.  Every thread calls both; between them only warps < NSOLVE work,
     // the others go straight to the closing barrier.
@@ -769,8 +780,8 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                 Hv[i] = H; Wv[i] = W;
             }
             if (live && valid) {
-                *reinterpret_cast<double2*>(wrow + k0) = make_double2(Wv[0], Wv[1]);
-                if (pm) *reinterpret_cast<double2*>(hrow + k0) = make_double2(Hv[0], Hv[1]);
+                st_keep_v2(wrow + k0, Wv[0], Wv[1], keep_pol);
+                if (pm) st_keep_v2(hrow + k0, Hv[0], Hv[1], keep_pol);
             }
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
@@ -1106,10 +1117,10 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                     if (a.o_nbatch) a.o_nbatch[o] = ctl.nbatch;
                     if (a.o_status) a.o_status[o] = (!hit_max && ctl.conv) ? MX_STATUS_CONVERGED : 0;
                 }
-                if (a.o_v) for (int i = tid; i < s; i += NTHR) a.o_v[o * s + i] = sm[LY::o_v + i];
+                if (a.o_v) for (int i = tid; i < s; i += NTHR) __stcs(a.o_v + o * s + i, sm[LY::o_v + i]);
                 if (a.o_A) {                                   // A = H / delta  (functions.py:947-952)
                     const double* hr = (pm ? hscr : wscr) + (size_t)ctl.cur_row * rowlen;
-                    for (int k = tid; k < a.n_omega; k += NTHR) a.o_A[o * a.n_omega + k] = hr[k] / a.delta[k];
+                    for (int k = tid; k < a.n_omega; k += NTHR) __stcs(a.o_A + o * a.n_omega + k, hr[k] / a.delta[k]);
                 }
                 __syncthreads();
                 if (tid == 0) {
