@@ -71,17 +71,19 @@ typedef struct {
     int32_t variant;          /* MX_VARIANT_*                                                */
     int32_t want_probability; /* NormalLogProbability (probabilities.py:76-85)               */
     int32_t engine;           /* MX_ENGINE_*                                                 */
-    int32_t reserved;         /* 0                                                           */
+    int32_t per_spectrum_model; /* 0: D[n_omega], v0[n_sv] shared by the batch; 1: D[B, ldD], v0[B, n_sv] with the row
+                               * stride ldD = n_omega rounded up to an even number (16-byte aligned rows)
+                               * (PoormanMaxEnt off-diagonals, python/elementwise_maxent.py:633-652)         */
     double  chi2_factor;      /* MaxEntCostFunction chi2_factor (cost_function.py:43-53)     */
     const double* Vt;         /* swizzled tile-major V' written by mx_layout_V               */
     const double* Qw;         /* [n_tau, n_sv]  sqrt(W) Q : g~ = Qw^T G                      */
     const double* Qo;         /* [n_tau, n_sv]  Q (orthonormal) for the out-of-range residual */
     const double* sqrtw;      /* [n_tau]        1/err                                         */
     const double* xi;         /* [n_sv]         singular values of sqrt(W) K V_s             */
-    const double* D;          /* [n_omega]      default model incl. delta omega              */
+    const double* D;          /* [n_omega] or [B, n_omega]  default model incl. delta omega  */
     const double* delta;      /* [n_omega]      trapezoid weights of the omega mesh          */
     const double* alpha;      /* [n_alpha]      alpha * scale_alpha, descending              */
-    const double* v0;         /* [n_sv]         initial v' (maxent_loop.py:196-203)          */
+    const double* v0;         /* [n_sv] or [B, n_sv]  initial v' (maxent_loop.py:196-203)    */
     MxLMParams lm;
 } MxProblem;
 

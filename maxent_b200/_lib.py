@@ -35,7 +35,7 @@ class MxLMParams(ctypes.Structure):
 class MxProblem(ctypes.Structure):
     _fields_ = [("n_tau", ctypes.c_int32), ("n_omega", ctypes.c_int32), ("n_sv", ctypes.c_int32),
                 ("n_alpha", ctypes.c_int32), ("variant", ctypes.c_int32), ("want_probability", ctypes.c_int32),
-                ("engine", ctypes.c_int32), ("reserved", ctypes.c_int32), ("chi2_factor", ctypes.c_double),
+                ("engine", ctypes.c_int32), ("per_spectrum_model", ctypes.c_int32), ("chi2_factor", ctypes.c_double),
                 ("Vt", c_dp), ("Qw", c_dp), ("Qo", c_dp), ("sqrtw", c_dp), ("xi", c_dp), ("D", c_dp),
                 ("delta", c_dp), ("alpha", c_dp), ("v0", c_dp), ("lm", MxLMParams)]
 

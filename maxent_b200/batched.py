@@ -199,12 +199,13 @@ class BatchedTauMaxEnt(object):
             return a * self.prepare().n_tau
         return a * float(self.scale_alpha)
 
-    def run_device(self, G_dev, want_A=True, want_v=False):
-        """Hot path on device-resident data: returns an engine.SweepResult of device tensors."""
+    def run_device(self, G_dev, want_A=True, want_v=False, D=None):
+        """Hot path on device-resident data: returns an engine.SweepResult of device tensors.
+        ``D`` [B, n_omega] (optional): one default model per spectrum, incl. delta omega like ``DefaultModel.D``."""
         prob = self.prepare()
         return engine.run_sweep(prob, G_dev, self.alpha_effective(), probability=self.probability is not None,
                                 lm=self.minimizer, want_A=want_A, want_v=want_v, gamma=self.gamma,
-                                linefit_deg=self.linefit_deg, bryan_by_integration=self.bryan_by_integration)
+                                linefit_deg=self.linefit_deg, bryan_by_integration=self.bryan_by_integration, D=D)
 
     def time_sweep_kernel(self, G_dev):
         """Milliseconds of the mx_alpha_sweep launch alone (CUDA events on the launching stream)."""
@@ -212,8 +213,9 @@ class BatchedTauMaxEnt(object):
         return engine.run_sweep(prob, G_dev, self.alpha_effective(), probability=self.probability is not None,
                                 lm=self.minimizer, want_A=True, want_v=False, time_kernel=True)
 
-    def run(self, G=None):
-        """Public call: host G[B, n_tau] in (numpy or pinned tensor), BatchedMaxEntResult (host arrays) out."""
+    def run(self, G=None, D=None):
+        """Public call: host G[B, n_tau] in (numpy or pinned tensor), BatchedMaxEntResult (host arrays) out.
+        ``D`` [B, n_omega] optionally gives every spectrum its own default model."""
         import torch
         G = self.G if G is None else G
         if G is None:
@@ -227,7 +229,7 @@ class BatchedTauMaxEnt(object):
         out.h2d_bytes = Gt.numel() * 8 if not Gt.is_cuda else 0
         with torch.cuda.device(dev):
             G_dev = Gt.to(dev, non_blocking=True)
-            res = self.run_device(G_dev)
+            res = self.run_device(G_dev, D=D)
             # spectra below the threshold are not continued by the reference (maxent_loop.py:174-179)
             small = (G_dev.abs().amax(dim=1) < self.G_threshold) if G_dev.shape[0] else None
             host = {}

@@ -291,6 +291,7 @@ static int fill_args(const MxProblem* p, SweepArgs& a) {
     a.maxiter = p->lm.maxiter; a.miniter = p->lm.miniter;
     a.mu0 = p->lm.mu0; a.nu = p->lm.nu; a.max_mu = p->lm.max_mu;
     a.conv_maxd = p->lm.conv_max_derivative; a.conv_relq = p->lm.conv_rel_change; a.eta = p->chi2_factor;
+    a.per_spec = p->per_spectrum_model ? 1 : 0;
     a.Vt = p->Vt; a.D = p->D; a.delta = p->delta; a.xi = p->xi; a.alpha = p->alpha; a.v0 = p->v0;
     return MX_OK;
 }

@@ -695,6 +695,7 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
     __syncthreads();
 
     const Pipe<NT> pipe{sm + LY::o_stage, a.Vt, bar_full, bar_empty, tid, lane, n_kt, nch};
+    const double* Dsp = a.D;
     const uint64_t keep_pol = l2_evict_last_policy();
 
     // Register hand-over around a solver phase.  Every thread calls both; between them only warps < NSOLVE work,
@@ -752,8 +753,8 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
             const int k0 = kt * 8 + 2 * q;
             double2 Dv = make_double2(0.0, 0.0);
             if (valid) {
-                if (k0 + 1 < a.n_omega) Dv = *reinterpret_cast<const double2*>(a.D + k0);
-                else if (k0 < a.n_omega) Dv.x = a.D[k0];
+                if (k0 + 1 < a.n_omega) Dv = *reinterpret_cast<const double2*>(Dsp + k0);
+                else if (k0 < a.n_omega) Dv.x = Dsp[k0];
             }
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
@@ -1055,14 +1056,16 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
         __syncthreads();
         const int sp = ctl.spec;
         if (sp >= a.B) break;
+        Dsp = a.D + (a.per_spec ? (size_t)sp * ((a.n_omega + 1) & ~1) : 0);       // per-spectrum default model (Poorman off-diagonals)
+        const double* const v0sp = a.v0 + (a.per_spec ? (size_t)sp * s : 0);
         for (int i = tid; i < SP; i += NTHR) {
-            const double v0 = i < s ? a.v0[i] : 0.0;
+            const double v0 = i < s ? v0sp[i] : 0.0;
             sm[LY::o_v + i] = v0;
             sm[LY::o_gt + i] = i < s ? a.gt[(size_t)sp * s + i] : 0.0;
         }
         for (int i = tid; i < MAXB * SP; i += NTHR) {
             const int b = i / SP, j = i - b * SP;
-            sm[LY::o_tb + i] = (b == 0 && j < s) ? a.v0[j] : 0.0;
+            sm[LY::o_tb + i] = (b == 0 && j < s) ? v0sp[j] : 0.0;
         }
         if (tid == 0) {
             ctl.ia = 0; ctl.it = 0; ctl.nq = 0; ctl.ns = 0; ctl.dir_up = 1; ctl.last_len = 99; ctl.ntrial = 1; ctl.nbatch = 1;

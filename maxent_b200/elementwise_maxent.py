@@ -107,11 +107,14 @@ class ElementwiseMaxEnt(object):
         self.put_error(worker, self.get_error((i, j)))
         return worker.maxent_loop.snapshot(matrix_element=(i, j), complex_index=0 if re else 1), worker
 
-    def _run_elements(self, elements):
-        """Continue a list of (element, re) pairs: jobs of the same worker go through ``run_jobs`` together."""
+    def _run_elements(self, elements, before=None):
+        """Continue a list of (element, re) pairs: jobs of the same worker go through ``run_jobs`` together.
+        ``before(element)`` is called ahead of loading each element (PoormanMaxEnt sets the default model there)."""
         self.prepare_maxent_result(overwrite=False)
         per_worker = {}
         for element, re in elements:
+            if before is not None:
+                before(element)
             job, worker = self._job(element, re)
             if job is not None:
                 per_worker.setdefault(id(worker), (worker, []))[1].append(job)
@@ -231,8 +234,8 @@ class DiagonalMaxEnt(ElementwiseMaxEnt):
 class PoormanMaxEnt(ElementwiseMaxEnt):
     """Poor man's matrix method: off-diagonal elements use the default model
     D_ij = sqrt(A_ii A_jj) + D_add_constant built from the diagonal results of ``analyzer_offdiag_D``.
-    Two phases with a barrier in between; every off-diagonal element has its own default model, i.e. its own
-    device problem, so the off-diagonal pass is one launch per element."""
+    Two phases with a barrier in between; every off-diagonal element has its own default model, passed to the
+    device as one model per spectrum, so the off-diagonal pass is a single launch."""
 
     def __init__(self, analyzer_offdiag_D='LineFitAnalyzer', D_add_constant=1.e-6, *args, **kwargs):
         super(PoormanMaxEnt, self).__init__(*args, **kwargs)
@@ -248,12 +251,11 @@ class PoormanMaxEnt(ElementwiseMaxEnt):
         def diag_A(i):
             node = ar[i][i][0] if self.use_complex else ar[i][i]
             return node[self.analyzer_offdiag_D]['A_out']
-        for i in range(self.shape[0]):
-            for j in range(self.shape[1]):
-                if i == j:
-                    continue
-                self.maxent_offdiagonal.set_D(DataDefaultModel(np.sqrt(diag_A(i) * diag_A(j)) + self.D_add_constant,
-                                                               self.omega))
-                for re in ([True, False] if self.use_complex else [True]):
-                    self.run_element((i, j), re=re)
-        return self.maxent_result
+
+        def set_model(element):
+            i, j = element
+            self.maxent_offdiagonal.set_D(DataDefaultModel(np.sqrt(diag_A(i) * diag_A(j)) + self.D_add_constant,
+                                                           self.omega))
+        # every element carries its own default model; they still share kernel and error model, so the whole
+        # off-diagonal pass is ONE launch with per-spectrum models (MxProblem.per_spectrum_model)
+        return self._run_elements(self._offdiagonal_elements(), before=set_model)

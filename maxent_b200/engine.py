@@ -116,6 +116,7 @@ class SharedProblem(object):
             self.D = torch.as_tensor(np.asarray(D, dtype=np.float64), dtype=f64, device=dev).contiguous()
             self.delta = torch.as_tensor(np.asarray(delta, dtype=np.float64), dtype=f64, device=dev).contiguous()
             # ---- initial v (python/maxent_loop.py:196-203; quirk: D*delta although D holds delta) ----
+            self.A_init_host = None if A_init is None else np.asarray(A_init, dtype=np.float64)
             H0 = (self.D if A_init is None else torch.as_tensor(np.asarray(A_init, dtype=np.float64), device=dev)) * self.delta
             if variant == "plusminus":
                 arg = (H0 + torch.sqrt(H0**2 + 4 * self.D**2)) / (2 * self.D)   # functions.py:793-796
@@ -237,11 +238,36 @@ def _dev_f64(x, dev):
     return torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64), device=dev)
 
 
-def _problem_struct(prob, alpha, probability, lm, chi2_factor):
+def _problem_struct(prob, alpha, probability, lm, chi2_factor, D_rows=None, v0_rows=None):
+    per = D_rows is not None
     return _lib.MxProblem(prob.n_tau, prob.n_omega, prob.n_sv, int(alpha.numel()), _lib.VARIANTS[prob.variant],
-                          int(bool(probability)), int(getattr(prob, "engine", 0)), 0, float(chi2_factor), _ptr(prob.Vt), _ptr(prob.Qw), _ptr(prob.Q),
-                          _ptr(prob.sqrtw), _ptr(prob.xi), _ptr(prob.D), _ptr(prob.delta), _ptr(alpha),
-                          _ptr(prob.v0), lm.c_struct())
+                          int(bool(probability)), int(getattr(prob, "engine", 0)), int(per), float(chi2_factor),
+                          _ptr(prob.Vt), _ptr(prob.Qw), _ptr(prob.Q), _ptr(prob.sqrtw), _ptr(prob.xi),
+                          _ptr(D_rows if per else prob.D), _ptr(prob.delta), _ptr(alpha),
+                          _ptr(v0_rows if per else prob.v0), lm.c_struct())
+
+
+def per_spectrum_models(prob, D, A_init=None):
+    """Device buffers for one default model PER SPECTRUM (MxProblem.per_spectrum_model = 1): D[B, n_omega] (incl.
+    delta omega, like DefaultModel.D) -> (D_rows[B, ldD], v0_rows[B, n_sv]); v0 = V'^T log(H0 / D) with
+    H0 = (D or A_init) * delta as in python/maxent_loop.py:196-203 (functions.py:753-755 / 793-796)."""
+    torch = _torch()
+    dev = prob.device
+    D = _dev_f64(D, dev)
+    B, n_omega = int(D.shape[0]), prob.n_omega
+    if D.shape[1] != n_omega:
+        raise ValueError("D has %d points, omega mesh has %d" % (D.shape[1], n_omega))
+    ld = (n_omega + 1) & ~1
+    D_rows = torch.zeros((B, ld), dtype=torch.float64, device=dev)
+    D_rows[:, :n_omega] = D
+    H0 = (D if A_init is None else _dev_f64(A_init, dev)) * prob.delta
+    if prob.variant == "plusminus":
+        arg = (H0 + torch.sqrt(H0 ** 2 + 4 * D ** 2)) / (2 * D)
+    else:
+        arg = H0 / D
+    arg = torch.where(arg.abs() <= 1e-100, torch.full_like(arg, 1e-100), arg)
+    v0_rows = (torch.log(arg) @ prob.Vp).contiguous()
+    return D_rows, v0_rows
 
 
 def project_data(prob, G):
@@ -289,7 +315,7 @@ def analyze(alpha, chi2, S, logp, A, gamma=0.2, linefit_deg=0, bryan_by_integrat
 
 
 def run_sweep(prob, G, alpha_eff, probability=False, lm=None, chi2_factor=1.0, want_A=True, want_v=True,
-              analyze_results=True, gamma=0.2, linefit_deg=0, bryan_by_integration=False, time_kernel=False):
+              analyze_results=True, gamma=0.2, linefit_deg=0, bryan_by_integration=False, time_kernel=False, D=None):
     """Fused alpha sweep for a batch G[B, n_tau] sharing `prob`.  `alpha_eff` = alpha * scale_alpha, descending.
     G may live on the host (numpy / pinned tensor: copied asynchronously) or on the device.
     Everything stays on the device; returns a SweepResult of torch tensors."""
@@ -308,7 +334,12 @@ def run_sweep(prob, G, alpha_eff, probability=False, lm=None, chi2_factor=1.0, w
         alpha = _dev_f64(np.asarray(alpha_eff, dtype=np.float64) if not torch.is_tensor(alpha_eff) else alpha_eff, dev)
         n_alpha, s, n_omega = int(alpha.numel()), prob.n_sv, prob.n_omega
         stream = _stream(dev)
-        p = _problem_struct(prob, alpha, probability, lm, chi2_factor)
+        D_rows = v0_rows = None
+        if D is not None:                    # one default model per spectrum, D[B, n_omega]
+            D_rows, v0_rows = per_spectrum_models(prob, D, getattr(prob, "A_init_host", None))
+            if D_rows.shape[0] != B:
+                raise ValueError("D has %d rows for %d spectra" % (D_rows.shape[0], B))
+        p = _problem_struct(prob, alpha, probability, lm, chi2_factor, D_rows, v0_rows)
         gt = torch.empty((B, s), dtype=f64, device=dev)
         c0 = torch.empty((B,), dtype=f64, device=dev)
         _lib.check(lib.mx_project_data(ctypes.byref(p), _ptr(G), B, _ptr(gt), _ptr(c0), stream), "mx_project_data")

@@ -91,14 +91,17 @@ class MaxEntLoop(object):
         variant = self.cost_function.variant() if variant is None else variant
         K = self.K
         err = np.asarray(self.err, dtype=np.float64) * np.ones(len(self.G))
-        key = (id(K), K._svd_version, variant, _bytes(err), _bytes(self.D.D), _bytes(self.omega.delta),
-               _bytes(self.A_init), str(self.device))
+        # the default model is NOT part of the key: jobs that differ only in D share the device problem and are
+        # continued in one launch with one default model per spectrum (PoormanMaxEnt's off-diagonal pass)
+        key = (id(K), K._svd_version, variant, _bytes(err), _bytes(self.omega.delta), _bytes(self.A_init),
+               str(self.device))
         prob = self._problem_cache.get(key)
         if prob is None:
             while len(self._problem_cache) >= 4:
                 self._problem_cache.pop(next(iter(self._problem_cache)))
             prob = engine.SharedProblem(K.K, err, self.D.D, self.omega.delta, variant=variant, device=self.device,
                                         A_init=self.A_init, usv=(K.U, K.S, K.V), orthonormal_U=K._T is None)
+            prob.D_host = np.array(self.D.D, dtype=np.float64)
             self._problem_cache[key] = prob
         return prob
 
@@ -117,6 +120,7 @@ class MaxEntLoop(object):
         self.K.reduce_singular_space(self.reduce_singular_space)
         self.check_consistency()
         job.update(problem=self.shared_problem(variant), scale=self._scale(), omega=self.omega,
+                   D=np.array(self.D.D, dtype=np.float64),
                    G_orig=np.array(self.cost_function.G_orig, dtype=np.float64),
                    data_variable=np.array(self.data_variable, dtype=np.float64), K_delta=self.K.K_delta)
         return job
@@ -153,9 +157,12 @@ class MaxEntLoop(object):
             alpha_eff = np.asarray(self.alpha_mesh, dtype=np.float64) * scale
             for job in group:
                 result.start_timing(matrix_element=job["matrix_element"], complex_index=job["complex_index"])
+            D_rows = np.stack([job["D"] for job in group])
+            if np.all(D_rows == prob.D_host[None, :]):
+                D_rows = None                                # the model the problem was built with: shared mode
             res = engine.run_sweep(prob, np.stack([job["G"] for job in group]), alpha_eff, probability=want_p, lm=lm,
                                    chi2_factor=self.cost_function.chi2_factor, want_A=True, want_v=True,
-                                   analyze_results=False)
+                                   analyze_results=False, D=D_rows)
             host = dict(A=res.A.cpu().numpy(), v=prob.v_to_reference_basis(res.v).cpu().numpy(),
                         chi2=res.chi2.cpu().numpy(), S=res.S.cpu().numpy(), Q=res.Q.cpu().numpy(),
                         logp=res.logp.cpu().numpy(), status=res.status.cpu().numpy(), n_iter=res.n_iter.cpu().numpy())

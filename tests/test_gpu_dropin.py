@@ -191,6 +191,18 @@ def test_poorman_runs_and_uses_diagonal_default_model():
     assert np.all(np.isfinite(res.A_out))
     # large alpha: the off-diagonal H = D(e^x - e^-x) stays near zero
     assert np.max(np.abs(res.A[0, 1, 0])) < np.max(np.abs(res.A[0, 1, -1])) + 1e-12
+    # the off-diagonal element went through the per-spectrum-model launch; a plain TauMaxEnt with that model agrees
+    tm = mb.TauMaxEnt(cost_function='plusminus')
+    tm.set_verbosity(mb.VerbosityFlags.Quiet)
+    tm.set_G_tau_data(g["tau"], g["G"][0, 1])
+    tm.omega = mb.DataOmegaMesh(g["omega"])
+    tm.alpha_mesh = mb.DataAlphaMesh(g["alpha_mesh"])
+    tm.D = mb.DataDefaultModel(np.sqrt(A00 * A11) + 1e-6, tm.omega)
+    tm.set_error(float(g["err"]))
+    r1 = tm.run()
+    k = res.analyzer_results[0][1]['LineFitAnalyzer']['alpha_index']
+    assert r1.analyzer_results['LineFitAnalyzer']['alpha_index'] == k
+    assert np.max(np.abs(r1.A[:k + 1] - res.A[0, 1, :k + 1])) <= 1e-7 * np.max(np.abs(r1.A[:k + 1]))
 
 
 def test_covariance_vs_error_vector():

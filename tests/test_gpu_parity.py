@@ -310,3 +310,35 @@ def test_full_size_properties(torch_cuda):
     assert np.all(np.abs(idx[:, 0] - 23) <= 1) and np.all(np.abs(idx[:, 1] - 28) <= 1)
     n_it = res.n_iter.sum(1).cpu().numpy()
     assert 400 < n_it.min() and n_it.max() < 2000          # 763-1196 per spectrum on 8 samples
+
+
+def test_per_spectrum_default_models(torch_cuda):
+    """MxProblem.per_spectrum_model: one default model per spectrum in ONE launch gives what separate launches
+    with a shared model give (PoormanMaxEnt's off-diagonal pass, python/elementwise_maxent.py:633-652), and the
+    oracle's numbers."""
+    from maxent_b200 import engine
+    rng = np.random.RandomState(4)
+    pr = mo.synthetic_problem(120, 75, beta=20.0, mu=[0.5, -0.7, 1.2], sigma=1e-3, seed=9)     # odd n_omega: padded rows
+    flat = mo.flat_default_model(pr["omega"])
+    w = pr["omega"]
+    models = np.stack([flat, flat * (1.0 + 0.5 * np.exp(-(w - 0.5) ** 2)), flat * (0.3 + rng.rand(75))])
+    mesh = mo.log_alpha_mesh(0.1, 300, 9)
+    for variant in ("normal", "plusminus"):
+        G = pr["G"] if variant == "normal" else pr["G"] - 0.7 * pr["G"][::-1]
+        prob = engine.SharedProblem(pr["K"], pr["err"], flat, pr["delta"], variant=variant, reduce_singular_space=1e-10)
+        res = engine.run_sweep(prob, G, mesh * 120, D=models)
+        for b in range(3):
+            pb = engine.SharedProblem(pr["K"], pr["err"], models[b], pr["delta"], variant=variant,
+                                      reduce_singular_space=1e-10)
+            one = engine.run_sweep(pb, G[b], mesh * 120)
+            o = mo.maxent_loop(pr["K"], G[b], pr["err"], pr["omega"], mesh, D=models[b], variant=variant,
+                               reduce_singular_space=1e-10, analyzers=False)
+            o2 = mo.maxent_loop(pr["K"], G[b] * (1 + 1e-15), pr["err"], pr["omega"], mesh, D=models[b], variant=variant,
+                                reduce_singular_space=1e-10, analyzers=False)
+            tol = np.maximum(1e-8, 10 * gc.running_max(gc.rel_A(o2["A"], o["A"])))
+            A = res.A[b].cpu().numpy()
+            assert np.all(gc.rel_A(A, o["A"]) <= tol), (variant, b, gc.rel_A(A, o["A"]) / tol)
+            assert np.all(gc.rel_A(A, one.A[0].cpu().numpy()) <= tol), (variant, b)
+            np.testing.assert_allclose(res.chi2[b].cpu().numpy(), o["chi2"], rtol=1e-7)
+    with pytest.raises(ValueError):
+        engine.run_sweep(prob, G, mesh * 120, D=models[:2])
