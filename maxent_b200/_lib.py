@@ -43,7 +43,7 @@ class MxProblem(ctypes.Structure):
 class MxSweepOut(ctypes.Structure):
     _fields_ = [("v", c_dp), ("A", c_dp), ("chi2", c_dp), ("S", c_dp), ("Q", c_dp), ("logp", c_dp),
                 ("n_iter", c_dp), ("n_qeval", c_dp), ("n_solve", c_dp), ("status", c_dp),
-                ("n_trial", c_dp), ("n_batch", c_dp)]
+                ("n_trial", c_dp), ("n_batch", c_dp), ("phase_cycles", c_dp)]
 
 
 # every symbol include/maxent_b200.h declares: (name, restype, argtypes)

@@ -1,5 +1,6 @@
 // C ABI of maxent_b200 (include/maxent_b200.h) + the small kernels around the alpha sweep:
 // V' re-tiling, TauKernel fill, data projection, analyzer reductions.
+#include <stdlib.h>
 #include "mx_common.cuh"
 #include <stdio.h>
 #include <stdint.h>
@@ -340,7 +341,7 @@ int mx_alpha_sweep(const MxProblem* p, const double* gt, const double* c0, int32
     a.B = B; a.gt = gt; a.c0 = c0;
     a.o_v = out->v; a.o_A = out->A; a.o_chi2 = out->chi2; a.o_S = out->S; a.o_Q = out->Q; a.o_logp = out->logp;
     a.o_niter = out->n_iter; a.o_nq = out->n_qeval; a.o_ns = out->n_solve; a.o_status = out->status;
-    a.o_ntrial = out->n_trial; a.o_nbatch = out->n_batch;
+    a.o_ntrial = out->n_trial; a.o_nbatch = out->n_batch; a.o_phase = reinterpret_cast<long long*>(out->phase_cycles);
     a.counter = reinterpret_cast<int*>(workspace);
     a.scratch = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + WS_HEADER);
     if (cudaMemsetAsync(workspace, 0, WS_HEADER, (cudaStream_t)stream) != cudaSuccess) return MX_ERR_CUDA;

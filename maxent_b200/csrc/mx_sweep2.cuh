@@ -26,6 +26,7 @@
 // V' streams L2 -> shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier, 4 stages) in the
 // swizzled 8x8-tile layout written by mx_layout_V.
 #pragma once
+#include <stdlib.h>
 #include "mx_common.cuh"
 
 namespace mx2 {
@@ -39,7 +40,13 @@ constexpr int NSOLVE = 4;       // warps that factorise (one warp group, see reg
 constexpr int NTHR = NWARP * 32;
 constexpr int REG_HI = 216, REG_LO = 40, REG_EVEN = 128;   // setmaxnreg budgets: 128 * (216 + 40) = 256 * 128
 constexpr int CH = 4;          // k-tiles (8 omega rows each) per staged chunk = one per warp in the T-pass
-constexpr int NSTAGE = 4;
+// Number of staging buffers of the V' stream.  The cost pass consumes two chunks per step, NST - 2 are in flight
+// while it computes.  Five and six stages (more bytes in flight) were measured on B200 and bought nothing: with one
+// CTA per SM the pass takes 18 us per batch against a DMMA-pipe bound of 9 us either way.  A diagnostic build that
+// skipped parts of the pass showed why: 7.5 us of it is the exp() of the 8 x n_omega trial points -- a dependent FP64
+// chain with only two evaluations in flight per thread and two to four warps per scheduler -- not the L2 -> SM stream
+// (an Estrin-scheme exp with half the chain depth was slower: it spills at the 128-register cap).
+__host__ __device__ constexpr int stage_count(int) { return 4; }
 constexpr int MAXB = 8;        // unique trials per batch = M of the MMA
 constexpr int NTAB = 32;       // damping values tabulated per batch (several may share one unique trial)
 constexpr int NROWS = 9;       // scratch rows per CTA: 8 trials + 1 carried candidate
@@ -135,8 +142,9 @@ struct Lay {
     static constexpr int SP = 8 * NT;
     static constexpr int NTRI = NT * (NT + 1) / 2;
     static constexpr int STAGE_D = CH * NT * 64;
-    static constexpr int o_stage = 0;                              // NSTAGE x STAGE_D ; aliases: Zfull [NT*NT*64], yred [NWARP][8][SP]
-    static constexpr int o_J = o_stage + NSTAGE * STAGE_D;         // NTRI tiles, C layout
+    static constexpr int NST = stage_count(NT);
+    static constexpr int o_stage = 0;                              // NST x STAGE_D ; aliases: Zfull [NT*NT*64], yred [NWARP][8][SP]
+    static constexpr int o_J = o_stage + NST * STAGE_D;         // NTRI tiles, C layout
     static constexpr int o_tb = o_J + NTRI * 64;                   // [8][SP] trial vectors t_b = v - dv_b
     static constexpr int o_dvb = o_tb + MAXB * SP;                 // [8][SP]
     static constexpr int o_yb = o_dvb + MAXB * SP;                 // [8][SP]
@@ -153,10 +161,10 @@ struct Lay {
     static constexpr int o_jd = o_ycur + SP;                       // diagonal of J
     static constexpr int o_sred = o_jd + SP;                       // [NWARP][8] entropy partials
     static constexpr int o_ctl = o_sred + NWARP * 8;                      // Ctl block (192 doubles reserved)
-    static constexpr int o_bar = o_ctl + 192;                      // 2*NSTAGE mbarriers
-    static constexpr int total = o_bar + 2 * NSTAGE;
-    static_assert(NT * NT * 64 <= NSTAGE * STAGE_D, "Zfull must fit in the staging area");
-    static_assert(NWARP * 8 * SP <= NSTAGE * STAGE_D, "yred must fit in the staging area");
+    static constexpr int o_bar = o_ctl + 192;                      // 2*NST mbarriers
+    static constexpr int total = o_bar + 2 * NST;
+    static_assert(NT * NT * 64 <= NST * STAGE_D, "Zfull must fit in the staging area");
+    static_assert(NWARP * 8 * SP <= NST * STAGE_D, "yred must fit in the staging area");
 };
 
 enum { PH_FIRST = 0, PH_PUMP, PH_PROBE, PH_WALK, PH_DONE };
@@ -182,7 +190,10 @@ struct Ctl {
     double jdmin;              // smallest |J_kk| (quick test for equivalent dampings)
     int spec, ia, it, nq, ns, dir_up, cur_row, action, conv, last_len, ns_it0, ntrial, nbatch;
     unsigned gchunk;           // chunks streamed so far (pipeline phase bookkeeping)
+    long long t_last;          // phase timers (clock64 of thread 0), see MX_PHASE_*
+    long long tph[8];
 };
+enum { PHT_PLAN = 0, PHT_SOLVE, PHT_TPASS, PHT_HPASS, PHT_GRAD, PHT_FORMJ, PHT_OTHER, PHT_OUT };
 static_assert(sizeof(Ctl) <= 192 * sizeof(double), "Ctl must fit its reserved block");
 
 // Levenberg-Marquardt damping search of one iteration, levenberg_minimizer.py:190-233, as a resumable
@@ -526,6 +537,7 @@ __device__ __forceinline__ void hpass_ktile(const double* __restrict__ tile0, do
 // ------------------------------------------------------------------------------------------
 template <int NT>
 struct Pipe {
+    static constexpr int NSTAGE = Lay<NT>::NST;
     double* stage0;
     const double* Vt;
     uint64_t* full;
@@ -548,13 +560,13 @@ struct Pipe {
             for (int c = 0; c < nprefetch && c < nch; ++c) issue(c, g0 + c);
         }
     }
-    // pair variant: chunks c and c+1 are consumed together; thread 0 first issues chunks c+2 and c+3, whose
-    // stages were released by every warp in the previous pair iteration
+    // pair variant: chunks c and c+1 are consumed together; thread 0 first issues the two chunks whose stages were
+    // released by every warp in the previous pair iteration (c + NSTAGE - 2 and c + NSTAGE - 1); begin() must have
+    // prefetched NSTAGE - 2 chunks
     __device__ __forceinline__ const double* wait2(int c, unsigned g0, const double*& second) const {
-        static_assert(NSTAGE == 4, "pair consumption assumes four stages");
         if (tid == 0) {
 #pragma unroll
-            for (int d = 2; d < 4; ++d) {
+            for (int d = NSTAGE - 2; d < NSTAGE; ++d) {
                 const int cn = c + d;
                 if (cn < nch) {
                     const unsigned gp = g0 + cn - NSTAGE;
@@ -657,15 +669,15 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
     constexpr bool LEAN = NT <= 7;
     constexpr bool REGSPLIT = NT == 8;
     using LN = Lean<NT>;
-    static_assert(!LEAN || NT * NT * 64 + 5 * LN::NSMT * 64 <= NSTAGE * LY::STAGE_D,
+    static_assert(!LEAN || NT * NT * 64 + 5 * LN::NSMT * 64 <= LY::NST * LY::STAGE_D,
                   "the parked tiles of warps 0-4 must not overlap Zfull (warp 0 factorises while Zfull is live)");
-    static_assert(!LEAN || NWARP * LN::NSMT * 64 <= NSTAGE * LY::STAGE_D, "parked tiles must fit in the staging area");
+    static_assert(!LEAN || NWARP * LN::NSMT * 64 <= LY::NST * LY::STAGE_D, "parked tiles must fit in the staging area");
     constexpr int SP = LY::SP;
     constexpr int NTRI = LY::NTRI;
     extern __shared__ __align__(128) double sm[];
     Ctl& ctl = *reinterpret_cast<Ctl*>(sm + LY::o_ctl);
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(sm + LY::o_bar);
-    uint64_t* bar_empty = bar_full + NSTAGE;
+    uint64_t* bar_empty = bar_full + LY::NST;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int r = lane >> 2, q = lane & 3;
     const int s = a.n_sv;
@@ -683,7 +695,7 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
     const int offY1 = tile_off(2 * q + 1, r);
 
     if (tid == 0) {
-        for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_full + i, 1); mbar_init(bar_empty + i, NWARP); }
+        for (int i = 0; i < LY::NST; ++i) { mbar_init(bar_full + i, 1); mbar_init(bar_empty + i, NWARP); }
         ctl.gchunk = 0;
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -696,6 +708,12 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
 
     const Pipe<NT> pipe{sm + LY::o_stage, a.Vt, bar_full, bar_empty, tid, lane, n_kt, nch};
     const double* Dsp = a.D;
+    // phase timers: thread 0 charges the cycles since the previous tick to phase k (only when the caller asked
+    // for them: MxSweepOut.phase_cycles)
+    const bool timing = a.o_phase != nullptr;
+    auto tick = [&](int k) {
+        if (timing && tid == 0) { const long long t = clock64(); ctl.tph[k] += t - ctl.t_last; ctl.t_last = t; }
+    };
     const uint64_t keep_pol = l2_evict_last_policy();
 
     // Register hand-over around a solver phase.  Every thread calls both; between them only warps < NSOLVE work,
@@ -720,7 +738,7 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
     auto tpass = [&]() {
         const unsigned g0 = ctl.gchunk;
         const int nuniq = ctl.nuniq;
-        pipe.begin(g0, 2);
+        pipe.begin(g0, LY::NST - 2);
         double tA[NT][2];
 #pragma unroll
         for (int jt = 0; jt < NT; ++jt) {
@@ -832,7 +850,7 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
     // ---- H-pass: Z = V'^T diag(w) V' with w from scratch row `row` -> Zfull (all NT x NT tiles, C layout) ----
     auto hpass = [&](int row) {
         const unsigned g0 = ctl.gchunk;
-        pipe.begin(g0, NSTAGE - 1);
+        pipe.begin(g0, LY::NST - 1);
         const int kg = warp >> 1, th = warp & 1;
         const double* wrow = wscr + (size_t)row * rowlen;
         double* Zf = sm + LY::o_stage;
@@ -931,7 +949,7 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
         const int nuniq = ctl.nuniq;
         if constexpr (LEAN) {
             // every warp factorises one shifted Hessian: eight trials per round
-            double* const Lsm = sm + LY::o_stage + NSTAGE * LY::STAGE_D - (warp + 1) * LN::NSMT * 64;
+            double* const Lsm = sm + LY::o_stage + LY::NST * LY::STAGE_D - (warp + 1) * LN::NSMT * 64;
             for (int u = warp; u < nuniq; u += NWARP) {
                 const double mu = ctl.umu[u];
                 auto load = [&](int I, int J) -> double2 {
@@ -1028,7 +1046,7 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
         bool ok = true;
         double ld = 0.0;
         if constexpr (LEAN) {
-            double* const Lsm = sm + LY::o_stage + NSTAGE * LY::STAGE_D - LN::NSMT * 64;     // warp 0's slice, beyond Zfull
+            double* const Lsm = sm + LY::o_stage + LY::NST * LY::STAGE_D - LN::NSMT * 64;     // warp 0's slice, beyond Zfull
             double R[LN::RDIM][2];
             lean_steps<NT, 0>(entry, Lsm, R, U, ok, ld, true, r, q, lane);
         } else {
@@ -1075,17 +1093,22 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
         }
         __syncthreads();
         // first evaluation at v0 (the reference's func_val = function(v), levenberg_minimizer.py:150)
+        if (timing && tid == 0) { ctl.t_last = clock64(); for (int k = 0; k < 8; ++k) ctl.tph[k] = 0; }
         tpass();
+        tick(PHT_TPASS);
         for (int i = tid; i < SP; i += NTHR) sm[LY::o_ycur + i] = sm[LY::o_yb + i];
         if (tid == 0) { ctl.chi2_cur = ctl.uchi2[0]; ctl.S_cur = ctl.uS[0]; ctl.cur_row = ctl.urow[0]; ctl.nq = 1; }
         __syncthreads();
 
         bool spectrum_done = false;
         while (!spectrum_done) {
+            tick(PHT_OTHER);
             hpass(ctl.cur_row);
+            tick(PHT_HPASS);
             // ---- convergence test / alpha loop (levenberg_minimizer.py:157-174, maxent_loop.py:241-266) ----
             for (;;) {
                 gradient();
+                tick(PHT_GRAD);
                 if (tid == 0) {
                     LM& L = ctl.lm;
                     L.Q1 = 0.5 * ctl.chi2_cur * a.eta - ctl.alpha * ctl.S_cur;
@@ -1135,10 +1158,19 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                     }
                 }
                 __syncthreads();
-                if (ctl.ia >= a.n_alpha) { spectrum_done = true; break; }
+                if (ctl.ia >= a.n_alpha) {
+                    if (timing && tid == 0) {
+                        tick(PHT_OUT);
+                        for (int k = 0; k < 8; ++k) a.o_phase[(size_t)sp * 8 + k] = ctl.tph[k];
+                    }
+                    spectrum_done = true;
+                    break;
+                }
             }
             if (spectrum_done) break;
+            tick(PHT_OUT);
             form_J();
+            tick(PHT_FORMJ);
             // ---- one Levenberg iteration: speculative batches until the damping search is decided ----
             if (tid == 0) { ctl.lm.Q0 = ctl.lm.Q1; ctl.lm.phase = PH_FIRST; ctl.nb = 0; ctl.nuniq = 0; ctl.urow[ID_CARRY] = -1; ctl.ns_it0 = ctl.ns; }
             __syncthreads();
@@ -1330,9 +1362,11 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                     if (lane == 0) { ctl.lm = L; ctl.ns = ns; ctl.nq = nq; ctl.conv = done; }
                 }
                 __syncthreads();
+                tick(PHT_PLAN);
                 if (ctl.conv) break;
                 for (int i = tid; i < MAXB * SP; i += NTHR) if (i >= ctl.nuniq * SP) sm[LY::o_tb + i] = 0.0;
                 solve_trials();
+                tick(PHT_SOLVE);
                 {
                     // every factorisation of the batch failed (J + mu not positive definite numerically, the early
                     // part of a pump): all Q are NaN by definition, no pass over V' is needed
@@ -1344,6 +1378,7 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                     } else {
                         tpass();
                     }
+                    tick(PHT_TPASS);
                 }
             }
             // ---- accept: v -= dv ; the accepted trial becomes the current point (levenberg_minimizer.py:239-243) ----
@@ -1381,7 +1416,9 @@ int launch_sweep2(const SweepArgs& a, cudaStream_t stream, bool query, int* o_sm
         if (cudaGetDevice(&dev) != cudaSuccess) { if (query) { if (o_grid) *o_grid = 0; return MX_OK; } return MX_ERR_NO_DEVICE; }
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    int grid = 2 * sms;
+    int per_sm = (NT <= 8) ? 2 : 1;
+    if (const char* e = getenv("MX_CTAS_PER_SM")) { if (e[0] == '1') per_sm = 1; }     // diagnostics: uncontended phase times
+    int grid = per_sm * sms;
     if (grid > a.B) grid = a.B;
     if (grid < 1) grid = 1;
     if (o_grid) *o_grid = grid;

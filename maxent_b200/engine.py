@@ -222,7 +222,7 @@ def svd_jacobi_host(K, device=None, max_sweeps=60):
 class SweepResult(object):
     """Device tensors produced by one call of the fused sweep (+ analyzers)."""
     __slots__ = ("alpha", "v", "A", "chi2", "S", "Q", "logp", "n_iter", "n_qeval", "n_solve", "status",
-                 "alpha_index", "A_out", "n_sv", "n_trial", "n_batch")
+                 "alpha_index", "A_out", "n_sv", "n_trial", "n_batch", "phase_cycles")
 
 
 def _stream(dev):
@@ -315,7 +315,8 @@ def analyze(alpha, chi2, S, logp, A, gamma=0.2, linefit_deg=0, bryan_by_integrat
 
 
 def run_sweep(prob, G, alpha_eff, probability=False, lm=None, chi2_factor=1.0, want_A=True, want_v=True,
-              analyze_results=True, gamma=0.2, linefit_deg=0, bryan_by_integration=False, time_kernel=False, D=None):
+              analyze_results=True, gamma=0.2, linefit_deg=0, bryan_by_integration=False, time_kernel=False, D=None,
+              phase_timers=False):
     """Fused alpha sweep for a batch G[B, n_tau] sharing `prob`.  `alpha_eff` = alpha * scale_alpha, descending.
     G may live on the host (numpy / pinned tensor: copied asynchronously) or on the device.
     Everything stays on the device; returns a SweepResult of torch tensors."""
@@ -358,6 +359,7 @@ def run_sweep(prob, G, alpha_eff, probability=False, lm=None, chi2_factor=1.0, w
         r.status = torch.zeros((B, n_alpha), dtype=i32, device=dev)
         r.n_trial = torch.zeros((B, n_alpha), dtype=i32, device=dev)
         r.n_batch = torch.zeros((B, n_alpha), dtype=i32, device=dev)
+        r.phase_cycles = torch.zeros((B, 8), dtype=torch.int64, device=dev) if phase_timers else None
         ws_bytes = int(lib.mx_sweep_workspace_bytes(ctypes.byref(p), B))
         if ws_bytes < 0:
             _lib.check(ws_bytes, "mx_sweep_workspace_bytes")
@@ -366,7 +368,7 @@ def run_sweep(prob, G, alpha_eff, probability=False, lm=None, chi2_factor=1.0, w
             ws = prob._workspace = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         out = _lib.MxSweepOut(_ptr(r.v), _ptr(r.A), _ptr(r.chi2), _ptr(r.S), _ptr(r.Q), _ptr(r.logp),
                               _ptr(r.n_iter), _ptr(r.n_qeval), _ptr(r.n_solve), _ptr(r.status),
-                              _ptr(r.n_trial), _ptr(r.n_batch))
+                              _ptr(r.n_trial), _ptr(r.n_batch), _ptr(r.phase_cycles))
         if time_kernel:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()

@@ -314,3 +314,41 @@ def test_config4_large_kernel_full_probability_analysis():
     br = res.analyzer_results['BryanAnalyzer']['A_out']
     assert np.all(br >= res.A.min(0) - 1e-12) and np.all(br <= res.A.max(0) + 1e-12)
     assert abs(np.trapezoid(res.A_out, np.asarray(tm.omega)) - 1.0) < 1e-2
+
+
+def test_complex_matrix_elements():
+    """use_complex=True (python/elementwise_maxent.py:244-268): real and imaginary parts of the off-diagonal
+    elements are continued separately (plus-minus entropy), the diagonal is real, A_out is Hermitian."""
+    g = gc.load_golden("g6_elementwise_2x2.npz")
+    tau, Gr = g["tau"], g["G"]
+    Gr = 0.5 * (Gr + np.transpose(Gr, (1, 0, 2)))               # the fixture's noise is independent per element
+    # a Hermitian G(tau): rotate the real symmetric matrix with a complex unitary
+    th = 0.3
+    U = np.array([[np.cos(th), 1j * np.sin(th)], [1j * np.sin(th), np.cos(th)]])
+    Gc = np.einsum('ab,bct,dc->adt', U, Gr.astype(complex), U.conj())
+    assert np.max(np.abs(Gc - np.conj(np.transpose(Gc, (1, 0, 2))))) < 1e-12
+    ew = mb.ElementwiseMaxEnt(use_hermiticity=True, use_complex=True)
+    ew.set_verbosity(mb.VerbosityFlags.Quiet)
+    ew.set_G_tau_data(tau, Gc)
+    ew.omega = mb.DataOmegaMesh(g["omega"])
+    ew.alpha_mesh = mb.DataAlphaMesh(g["alpha_mesh"])
+    ew.set_error(float(g["err"]))
+    res = ew.run()
+    assert res.effective_matrix_structure == (2, 2, 2) and res.A.shape == (2, 2, 2, 8, 80)
+    assert (0, 0, 1) in res.zero_elements and (1, 1, 1) in res.zero_elements
+    A_out = res.A_out
+    assert A_out.dtype == complex and A_out.shape == (2, 2, 80)
+    np.testing.assert_array_equal(A_out[1, 0], np.conj(A_out[0, 1]))
+    assert np.max(np.abs(A_out[0, 0].imag)) == 0 and np.all(np.isfinite(A_out.real))
+    # trace is invariant under the rotation: compare with the real run's diagonal sum at the LineFit alphas
+    ref = mb.ElementwiseMaxEnt(use_hermiticity=True)
+    ref.set_verbosity(mb.VerbosityFlags.Quiet)
+    ref.set_G_tau_data(tau, Gr)
+    ref.omega = mb.DataOmegaMesh(g["omega"])
+    ref.alpha_mesh = mb.DataAlphaMesh(g["alpha_mesh"])
+    ref.set_error(float(g["err"]))
+    r0 = ref.run()
+    om = np.asarray(ew.omega)
+    t_c = np.trapezoid((A_out[0, 0] + A_out[1, 1]).real, om)
+    t_r = np.trapezoid(r0.A_out[0, 0] + r0.A_out[1, 1], om)
+    assert abs(t_c - t_r) < 2e-2 and abs(t_c - 2.0) < 5e-2
