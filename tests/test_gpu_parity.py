@@ -342,3 +342,38 @@ def test_per_spectrum_default_models(torch_cuda):
             np.testing.assert_allclose(res.chi2[b].cpu().numpy(), o["chi2"], rtol=1e-7)
     with pytest.raises(ValueError):
         engine.run_sweep(prob, G, mesh * 120, D=models[:2])
+
+
+@pytest.mark.parametrize("n_sv_target", [45, 62, 70, 78])
+def test_all_kernel_instantiations_vs_oracle(torch_cuda, n_sv_target):
+    """Every tile count of the sweep kernel (NT = ceil(n_sv / 8): lean 8-warp solver up to 56, register-split
+    solver up to 64, one CTA per SM above) on a DataKernel whose singular values decay slowly, vs the oracle."""
+    from maxent_b200 import engine
+    rng = np.random.RandomState(100 + n_sv_target)
+    n_tau, n_om = 140, 96
+    om = mo.linear_omega_mesh(-4, 4, n_om)
+    tau = np.linspace(0, 1, n_tau)
+    # smooth positive kernel + a random part so that exactly n_sv_target singular values pass the cut
+    U, _ = np.linalg.qr(rng.randn(n_tau, n_om))
+    V, _ = np.linalg.qr(rng.randn(n_om, n_om))
+    S = np.concatenate([np.logspace(0, -6, n_sv_target), 1e-14 * np.ones(n_om - n_sv_target)])
+    K = (U * S) @ V.T
+    A_true = np.exp(-(om - 0.5) ** 2) + 0.5 * np.exp(-(om + 1.5) ** 2 / 0.5)
+    delta = mo.omega_delta(om)
+    G = (K * delta[None, :]) @ A_true + 1e-4 * rng.randn(2, n_tau)
+    D = mo.flat_default_model(om)
+    mesh = mo.log_alpha_mesh(0.5, 500, 7)
+    prob = engine.SharedProblem(K, 1e-4, D, delta, reduce_singular_space=1e-9)
+    assert prob.n_sv == n_sv_target
+    res = engine.run_sweep(prob, G, mesh * n_tau, probability=True)
+    for b in range(2):
+        o = mo.maxent_loop(K, G[b], 1e-4, om, mesh, probability=True, reduce_singular_space=1e-9, analyzers=False)
+        o2 = mo.maxent_loop(K, G[b] * (1 + 1e-15), 1e-4, om, mesh, reduce_singular_space=1e-9, analyzers=False)
+        assert o["n_sv"] == n_sv_target
+        tol = np.maximum(1e-8, 10 * gc.running_max(gc.rel_A(o2["A"], o["A"])))
+        dA = gc.rel_A(res.A[b].cpu().numpy(), o["A"])
+        assert np.all(dA <= tol), (n_sv_target, b, dA / tol)
+        np.testing.assert_allclose(res.chi2[b].cpu().numpy(), o["chi2"], rtol=1e-7)
+        p = res.logp[b].cpu().numpy()
+        assert np.all(np.abs(p - o["probability"]) <= 1e-6 * np.abs(o["probability"]))
+    assert bool((res.status & 1).all())
