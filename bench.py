@@ -32,7 +32,7 @@ UNIT = "spectra/s"
 # DMMA m8n8k4 and DFMA both saturate at 37.0 TFLOP/s).  MEASURED_PEAKS.json holds no FP64 figure.
 FP64_PEAK_FALLBACK_TFLOPS = 37.0
 # DRAM traffic of the sweep kernel from the ncu capture under profiles/ (bytes read + written, per spectrum)
-NCU_DRAM_BYTES_PER_SPECTRUM = int((13.916928e6 + 4.816254e9) / 296)   # profiles/r01b_sweep2_ncu_full_summary.json
+NCU_DRAM_BYTES_PER_SPECTRUM = int((3.665920e6 + 795.489024e6) / 296)   # profiles/r01c_sweep2_ncu_full_summary.json
 
 
 def parse_args():
