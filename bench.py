@@ -193,6 +193,8 @@ def run_native(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL writes its banner / debug lines to stdout by default; stdout carries the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- the job: one BatchedTauMaxEnt per rank over its shard of the bootstrap batch ------------
@@ -271,6 +273,7 @@ def run_native(a):
     gather_ms = 0.0
     if world > 1:
         # the one collective of the job: gather the analyzer outputs on rank 0 (NCCL over NVLink), once per job
+        batched.gather_results(out, dst=0)              # first call sets up the NCCL connections
         barrier()
         t_g = time.time()
         gathered = batched.gather_results(out, dst=0)

@@ -282,6 +282,12 @@ def gather_results(out, dst=0):
             parts = [torch.empty((int(n),) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device) for n in sizes]
         else:
             parts = None
+        if all(int(n) == int(sizes[0]) for n in sizes):
+            # equal shards (the benchmark's case): one gather collective
+            dist.gather(t, parts, dst=dst)
+            if rank == dst:
+                got[name] = torch.cat(parts, 0).cpu().numpy()
+            continue
         # ragged shards: point-to-point gather
         if rank == dst:
             for r in range(world):

@@ -46,7 +46,7 @@ def _worker(rank, world, port, n_total, tmp):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_total", [11, 1])
+@pytest.mark.parametrize("n_total", [11, 1, 8])
 def test_two_rank_gather_over_gloo(tmp_path, n_total):
     import torch.multiprocessing as mp
     port = _free_port()
