@@ -352,3 +352,36 @@ def test_complex_matrix_elements():
     t_c = np.trapezoid((A_out[0, 0] + A_out[1, 1]).real, om)
     t_r = np.trapezoid(r0.A_out[0, 0] + r0.A_out[1, 1], om)
     assert abs(t_c - t_r) < 2e-2 and abs(t_c - 2.0) < 5e-2
+
+
+def test_maxent_loop_with_data_kernel():
+    """A user-supplied kernel matrix (DataKernel, python/kernels.py:183-207) through a hand-assembled MaxEntLoop,
+    against the oracle; also Bryan's cost function on the same problem (test/python/bryan_cost_function.py)."""
+    from oracle import maxent_oracle as mo
+    rng = np.random.RandomState(21)
+    n_tau, n_om = 90, 64
+    om = mb.LinearOmegaMesh(-3, 3, n_om)
+    U, _ = np.linalg.qr(rng.randn(n_tau, n_om))
+    V, _ = np.linalg.qr(rng.randn(n_om, n_om))
+    S = np.concatenate([np.logspace(0, -5, 40), 1e-15 * np.ones(n_om - 40)])
+    Kmat = (U * S) @ V.T
+    A_true = np.exp(-(np.asarray(om) - 0.3) ** 2)
+    G = (Kmat * om.delta[None, :]) @ A_true + 1e-3 * rng.randn(n_tau)
+    mesh = mb.LogAlphaMesh(0.5, 200, 6)
+    for kind, variant in (('normal', 'normal'), ('bryan', 'bryan')):
+        K = mb.DataKernel(np.arange(n_tau, dtype=float), om, Kmat)
+        D = mb.FlatDefaultModel(om)
+        ml = mb.MaxEntLoop(cost_function=kind, alpha_mesh=mesh, reduce_singular_space=1e-9)
+        ml.set_verbosity(mb.VerbosityFlags.Quiet)
+        ml.K, ml.D, ml.G, ml.err = K, D, G, 1e-3 * np.ones(n_tau)
+        res = ml.run()
+        assert len(K.S) == 40 and np.all(res.converged)
+        o = mo.maxent_loop(Kmat, G, 1e-3, np.asarray(om), np.asarray(mesh), variant=variant, reduce_singular_space=1e-9)
+        o2 = mo.maxent_loop(Kmat, G * (1 + 1e-15), 1e-3, np.asarray(om), np.asarray(mesh), variant=variant,
+                            reduce_singular_space=1e-9, analyzers=False)
+        tol = np.maximum(1e-8, 10 * gc.running_max(gc.rel_A(o2["A"], o["A"])))
+        assert np.all(gc.rel_A(res.A, o["A"]) <= tol), (kind, gc.rel_A(res.A, o["A"]) / tol)
+        np.testing.assert_allclose(res.chi2, o["chi2"], rtol=1e-7)
+        for name in ('LineFitAnalyzer', 'Chi2CurvatureAnalyzer', 'EntropyAnalyzer'):
+            assert res.analyzer_results[name]['alpha_index'] == o["analyzers"][name]["alpha_index"]
+        np.testing.assert_allclose(res.G_rec[-1], (Kmat * om.delta[None, :]) @ res.A[-1], rtol=1e-12)

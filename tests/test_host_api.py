@@ -272,3 +272,27 @@ def _mock_result():
     res = mb.MaxEntResult()
     res.add_sweep(_record(8, 4, 3, 5))
     return res
+
+
+def test_file_setters(tmp_path):
+    """set_G_tau_file / set_cov_file read text files like the reference (python/tau_maxent.py:198-225,290-301)."""
+    tau = np.linspace(0, 4, 9)
+    G = -np.exp(-tau)
+    err = 0.01 * (1 + tau)
+    f = tmp_path / "g.dat"
+    np.savetxt(str(f), np.column_stack([tau, G, err]))
+    tm = mb.TauMaxEnt()
+    tm.set_G_tau_file(str(f), tau_col=0, G_col=1, err_col=2)
+    np.testing.assert_allclose(tm.tau, tau)
+    np.testing.assert_allclose(tm.G, G)
+    np.testing.assert_allclose(tm.err, err)
+    tm2 = mb.TauMaxEnt()
+    tm2.set_G_tau_file(str(f))
+    assert tm2.err is None and len(tm2.G) == 9
+    ew = mb.ElementwiseMaxEnt()
+    ew.set_G_tau_filenames([[str(f), str(f)], [str(f), str(f)]])
+    assert ew.shape == (2, 2)
+    ew.set_G_element(ew.maxent_diagonal, ew.G_mat, (1, 1), True)
+    np.testing.assert_allclose(ew.maxent_diagonal.G, G)
+    ew.set_G_tau_filename_pattern(str(tmp_path / "g_{i}_{j}.dat"), (3, 3))
+    assert ew.shape == (3, 3)
