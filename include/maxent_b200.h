@@ -102,7 +102,8 @@ typedef struct {
     int32_t* n_trial;  /* [B, n_alpha]   trial points the device evaluated (incl. mis-speculated ones); may be NULL */
     int32_t* n_batch;  /* [B, n_alpha]   speculative batches (= passes over V' for cost evaluations); may be NULL */
     int64_t* phase_cycles; /* [B, 8]     SM clock cycles per spectrum spent in: planner, solver, T-pass, H-pass, gradient,
-                            *             J assembly, other, output/convergence (diagnostics; may be NULL)              */
+                            *             J assembly, other (accept, convergence test, outputs), replay of the damping
+                            *             search on the tabulated trials (diagnostics; may be NULL)                     */
 } MxSweepOut;
 
 /* Library / device info.  Returns the number of SMs of the current device (or <0). */

@@ -193,7 +193,7 @@ struct Ctl {
     long long t_last;          // phase timers (clock64 of thread 0), see MX_PHASE_*
     long long tph[8];
 };
-enum { PHT_PLAN = 0, PHT_SOLVE, PHT_TPASS, PHT_HPASS, PHT_GRAD, PHT_FORMJ, PHT_OTHER, PHT_OUT };
+enum { PHT_PLAN = 0, PHT_SOLVE, PHT_TPASS, PHT_HPASS, PHT_GRAD, PHT_FORMJ, PHT_OTHER, PHT_REPLAY };
 static_assert(sizeof(Ctl) <= 192 * sizeof(double), "Ctl must fit its reserved block");
 
 // Levenberg-Marquardt damping search of one iteration, levenberg_minimizer.py:190-233, as a resumable
@@ -774,11 +774,22 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                 if (k0 + 1 < a.n_omega) Dv = *reinterpret_cast<const double2*>(Dsp + k0);
                 else if (k0 < a.n_omega) Dv.x = Dsp[k0];
             }
+            // the two (plus-minus: four) exponentials of this lane as independent straight-line chains; the rare
+            // huge arguments (overflowing pump trials) take the library path
+            const double x0 = C0[0] + C1[0], x1 = C0[1] + C1[1];
+            double ex2[2], em2[2] = {0.0, 0.0};
+            if (__any_sync(0xffffffffu, mx::exp_is_special(x0) || mx::exp_is_special(x1))) {
+                ex2[0] = exp(x0); ex2[1] = exp(x1);
+                if (pm) { em2[0] = exp(-x0); em2[1] = exp(-x1); }
+            } else {
+                ex2[0] = mx::exp_main(x0); ex2[1] = mx::exp_main(x1);
+                if (pm) { em2[0] = mx::exp_main(-x0); em2[1] = mx::exp_main(-x1); }
+            }
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 const double Dk = i ? Dv.y : Dv.x;
-                const double x = C0[i] + C1[i];
-                const double ex = exp(x);
+                const double x = i ? x1 : x0;
+                const double ex = ex2[i];
                 double H, W, st_;
                 if (!pm) {
                     // H = D e^x ; S += H - D - H log(H/D), safelog clamp at 1e-100  (functions.py:53-56,508-510)
@@ -787,7 +798,7 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                     st_ = H - Dk - H * lg;
                 } else {
                     // H = D (e^x - e^-x) ; w = D (e^x + e^-x) ; S = S_n(H+) + S_n(H-)   (functions.py:544-564,778-786)
-                    const double em = exp(-x);
+                    const double em = em2[i];
                     const double Hp = Dk * ex, Hm = Dk * em;
                     H = Hp - Hm; W = Hp + Hm;
                     const double lp = (ex <= 1e-100) ? -230.25850929940458 : x;
@@ -1160,7 +1171,7 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                 __syncthreads();
                 if (ctl.ia >= a.n_alpha) {
                     if (timing && tid == 0) {
-                        tick(PHT_OUT);
+                        tick(PHT_OTHER);
                         for (int k = 0; k < 8; ++k) a.o_phase[(size_t)sp * 8 + k] = ctl.tph[k];
                     }
                     spectrum_done = true;
@@ -1168,7 +1179,7 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                 }
             }
             if (spectrum_done) break;
-            tick(PHT_OUT);
+            tick(PHT_OTHER);
             form_J();
             tick(PHT_FORMJ);
             // ---- one Levenberg iteration: speculative batches until the damping search is decided ----
@@ -1225,6 +1236,7 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                         return true;
                     };
                     const int done = lm_run(L, a.nu, a.max_mu, eps_nu, look_real) ? 1 : 0;
+                    tick(PHT_REPLAY);
                     if (!done) {
                         // carry the live candidate of the old batch (its dv, y, chi2, S, damping and scratch row)
                         const int live = (L.phase == PH_WALK) ? L.dvnew : (L.phase == PH_PROBE ? L.dv : ID_NONE);

@@ -18,7 +18,7 @@ job.set_alpha_mesh_log(0.01, 2000.0, 60)
 job.set_error(1.e-4)
 prob = job.prepare()
 Gd = G.cuda()
-names = ["planner", "solver", "T-pass", "H-pass", "gradient", "J assembly", "accept/other", "convergence/output"]
+names = ["planner", "solver", "T-pass", "H-pass", "gradient", "J assembly", "accept/convergence/output", "replay"]
 out = {}
 for per_sm in ("2", "1"):
     os.environ["MX_CTAS_PER_SM"] = per_sm
