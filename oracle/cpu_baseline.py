@@ -50,15 +50,18 @@ def _one(b):
     out = mo.maxent_loop(pr["K"], pr["G"][b], pr["err"], pr["omega"], _P["mesh"],
                          reduce_singular_space=_P["thr"], fast_d2=True)
     an = out["analyzers"]
-    return dict(b=b, wall=time.perf_counter() - t0, n_iter=int(out["n_iter"].sum()), n_qeval=int(out["n_qeval"]),
+    if _P.get("keep"):
+        _P["keep_rows"] = dict(A=out["A"], chi2=out["chi2"], S=out["S"], Q=out["Q"], n_iter=out["n_iter"])
+    return dict(b=b, arrays=_P.pop("keep_rows", None), wall=time.perf_counter() - t0, n_iter=int(out["n_iter"].sum()), n_qeval=int(out["n_qeval"]),
                 n_solve=int(out["n_solve"]), n_sv=int(out["n_sv"]),
                 linefit=int(an["LineFitAnalyzer"]["alpha_index"]), chi2curv=int(an["Chi2CurvatureAnalyzer"]["alpha_index"]))
 
 
-def run(n_tau, n_omega, n_alpha, spectra, procs, thr=1e-11, seed=5):
+def run(n_tau, n_omega, n_alpha, spectra, procs, thr=1e-11, seed=5, dump=None):
     import multiprocessing as mp
     ctx = mp.get_context("fork")
     t0 = time.perf_counter()
+    _P["keep"] = dump is not None            # inherited by the forked workers
     if procs <= 1:
         _init(n_tau, n_omega, n_alpha, spectra, thr, seed)
         rows = [_one(b) for b in range(spectra)]
@@ -66,6 +69,12 @@ def run(n_tau, n_omega, n_alpha, spectra, procs, thr=1e-11, seed=5):
         with ctx.Pool(procs, initializer=_init, initargs=(n_tau, n_omega, n_alpha, spectra, thr, seed)) as pool:
             rows = pool.map(_one, range(spectra), chunksize=1)
     wall = time.perf_counter() - t0
+    if dump is not None:                     # the oracle's own outputs, for the full-size parity test
+        pr = bench_inputs(n_tau, n_omega, spectra, seed)
+        np.savez(dump, G=pr["G"], A=np.stack([r["arrays"]["A"] for r in rows]), chi2=np.stack([r["arrays"]["chi2"] for r in rows]),
+                 S=np.stack([r["arrays"]["S"] for r in rows]), Q=np.stack([r["arrays"]["Q"] for r in rows]),
+                 n_iter=np.stack([r["arrays"]["n_iter"] for r in rows]), linefit=np.array([r["linefit"] for r in rows]),
+                 chi2curv=np.array([r["chi2curv"] for r in rows]))
     return dict(spectra=spectra, wall_s=wall, spectra_per_s=spectra / wall, cores=procs,
                 per_spectrum_s=[round(r["wall"], 3) for r in rows], n_iter=[r["n_iter"] for r in rows],
                 n_qeval=[r["n_qeval"] for r in rows], n_solve=[r["n_solve"] for r in rows], n_sv=rows[0]["n_sv"],
@@ -82,10 +91,11 @@ def main():
     ap.add_argument("--spectra", type=int, default=0)
     ap.add_argument("--procs", type=int, default=0)
     ap.add_argument("--thr", type=float, default=1e-11)
+    ap.add_argument("--dump", default=None, help="write the oracle's A/chi2/S/Q/picks of the sample to this .npz")
     a = ap.parse_args()
     procs = a.procs or (os.cpu_count() or 1)
     spectra = a.spectra or procs
-    print(json.dumps(run(a.n_tau, a.n_omega, a.n_alpha, spectra, procs, a.thr)))
+    print(json.dumps(run(a.n_tau, a.n_omega, a.n_alpha, spectra, procs, a.thr, dump=a.dump)))
 
 
 if __name__ == "__main__":

@@ -377,3 +377,36 @@ def test_all_kernel_instantiations_vs_oracle(torch_cuda, n_sv_target):
         p = res.logp[b].cpu().numpy()
         assert np.all(np.abs(p - o["probability"]) <= 1e-6 * np.abs(o["probability"]))
     assert bool((res.status & 1).all())
+
+
+def test_full_size_sample_vs_oracle(torch_cuda, tmp_path):
+    """BASELINE config 3/5 shape (n_tau = 2000, n_omega = 1000, 60 alphas, cut 1e-11): the first four spectra of the
+    benchmark batch against the oracle run on the host cores (one process per spectrum, ~30 s).  Tolerances follow the
+    reference's own reproducibility at this shape (A_alpha reproducible to <= 2e-11 up to alpha
+    index 36, 4e-9 ... 4e-5 in the small-alpha tail): identical LineFit / Chi2Curvature picks, A and chi2 within 1e-8
+    for alpha index <= 36, the tail within 1e-3 (A) / 1e-6 (chi2)."""
+    import os, subprocess, sys
+    from maxent_b200 import engine
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dump = str(tmp_path / "oracle_full.npz")
+    n = 4
+    subprocess.run([sys.executable, "-m", "oracle.cpu_baseline", "--n-tau", "2000", "--n-omega", "1000", "--n-alpha", "60",
+                    "--spectra", str(n), "--procs", str(n), "--thr", "1e-11", "--dump", dump], cwd=root, check=True,
+                   capture_output=True)
+    o = np.load(dump)
+    pr = mo.synthetic_problem(2000, 1000, mu=np.ones(1), noise=np.zeros((1, 2000)))
+    D = mo.flat_default_model(pr["omega"])
+    prob = engine.SharedProblem(pr["K"], pr["err"], D, pr["delta"], reduce_singular_space=1e-11)
+    alpha = mo.log_alpha_mesh(0.01, 2000, 60) * 2000
+    res = engine.run_sweep(prob, o["G"], alpha)
+    A = res.A.cpu().numpy()
+    idx = res.alpha_index.cpu().numpy()
+    for b in range(n):
+        assert idx[b, 0] == o["linefit"][b] and idx[b, 1] == o["chi2curv"][b], (b, idx[b, :2], o["linefit"][b], o["chi2curv"][b])
+        dA = gc.rel_A(A[b], o["A"][b])
+        assert np.all(dA[:37] <= 1e-8), (b, dA[:37].max(), int(dA[:37].argmax()))
+        assert np.all(dA <= 1e-3), (b, dA.max())
+        dc = np.abs(res.chi2[b].cpu().numpy() / o["chi2"][b] - 1)
+        assert np.all(dc[:37] <= 1e-8) and np.all(dc <= 1e-6), (b, dc.max())
+        for k in (idx[b, 0], idx[b, 1]):
+            assert dA[k] <= 1e-8
