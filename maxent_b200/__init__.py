@@ -25,6 +25,7 @@ from .analyzers import (Analyzer, AnalyzerResult, LineFitAnalyzer, Chi2Curvature
                         ClassicAnalyzer, BryanAnalyzer)
 from .maxent_result import MaxEntResult, MaxEntResultData
 from .maxent_loop import MaxEntLoop
+from .preblur import get_preblur
 from .tau_maxent import TauMaxEnt
 from .elementwise_maxent import ElementwiseMaxEnt, DiagonalMaxEnt, PoormanMaxEnt, CallableMethodCheck
 from .batched import BatchedTauMaxEnt, BatchedMaxEntResult

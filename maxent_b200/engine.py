@@ -196,6 +196,16 @@ def tau_kernel_host(tau, omega, beta, device=None):
         return K.cpu().numpy()
 
 
+def matmul_host(A, B, device=None):
+    """A @ B on the device (plain library GEMM, problem set-up only: K diag(delta) B of the preblur kernel);
+    numpy in, numpy out."""
+    torch = _require_cuda()
+    dev = torch.device("cuda" if device is None else device)
+    with torch.cuda.device(dev):
+        return (torch.as_tensor(np.ascontiguousarray(A, dtype=np.float64), device=dev)
+                @ torch.as_tensor(np.ascontiguousarray(B, dtype=np.float64), device=dev)).cpu().numpy()
+
+
 def svd_jacobi_host(K, device=None, max_sweeps=60):
     """Thin SVD K = U diag(S) V^T by the device one-sided Jacobi (mx_svd_jacobi), replacing np.linalg.svd in
     KernelSVD.svd (python/kernels.py:53-64).  numpy in, numpy (U[m,k], S[k], V[n,k]) out, k = min(m, n)."""

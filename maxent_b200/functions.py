@@ -14,7 +14,7 @@ device kernel (``MX_VARIANT_*``); the arithmetic itself lives in csrc/mx_sweep2.
 
 Evaluating one of them on the host (``chi2(H).f()`` ...) is deliberately not offered: there is no CPU
 implementation of the hot path in this package.  Variants that the fused path does not cover
-(complex chi2 / entropies, NoExp / Identity H(v), preblur) raise ``NotImplementedError`` on construction."""
+(complex chi2 / entropies, NoExp / Identity H(v)) raise ``NotImplementedError`` on construction."""
 import numpy as np
 
 
@@ -248,4 +248,32 @@ class IdentityA_of_H(GenericA_of_H):
     """A = H / delta omega (python/functions.py:947-952); applied by the sweep kernel when it writes A."""
 
 
-PreblurA_of_H = _unsupported("PreblurA_of_H", "SURVEY.md 8(f) rank 3")
+class PreblurA_of_H(GenericA_of_H):
+    """A = B H (python/functions.py:967-1023): the output map of the preblur formalism.  The sweep kernel works on
+    the hidden image H; the blur is applied to its H_alpha on the device when the results are collected
+    (maxent_loop.run_jobs).  Use together with ``PreblurKernel``."""
+
+    def __init__(self, b, omega):
+        self._omega = omega
+        self._b = b
+        self.parameter_change()
+
+    def parameter_change(self):
+        from .preblur import get_preblur
+        self._B = get_preblur(self._omega, self._b)
+
+    def set_omega(self, omega):
+        self._omega = omega
+        self.parameter_change()
+
+    omega = property(GenericA_of_H.get_omega, set_omega)
+
+    def get_b(self):
+        return self._b
+
+    def set_b(self, b, update_A_of_H=True):
+        self._b = b
+        if update_A_of_H:
+            self.parameter_change()
+
+    b = property(get_b, set_b)

@@ -88,6 +88,7 @@ class Kernel(KernelSVD):
         self._T = None
         self._K_delta = None
 
+
     @property
     def K_delta(self):
         """K times delta omega, in the ORIGINAL (unrotated) data basis: G_rec = K_delta A."""
@@ -203,7 +204,51 @@ class IOmegaKernel(Kernel):
 
 
 class PreblurKernel(Kernel):
-    """Preblur kernel K.B (python/kernels.py:349-413): SURVEY.md 8(f) rank 3, not built yet."""
+    """Kernel of the preblur formalism (python/kernels.py:349-413): K_pb = K diag(delta omega) B, so that
+    G = K_pb H for a hidden image H (which carries a delta omega) and A = B H.  Wraps another kernel (e.g. a
+    TauKernel); always use it together with ``PreblurA_of_H(b, omega)``.  ``K_delta`` is the inner kernel's."""
 
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError("PreblurKernel is not on the fused B200 path yet")
+    def __init__(self, K, b):
+        KernelSVD.__init__(self)
+        self._T = None
+        self.kernel = K
+        self._b = b
+        self._fill_values()
+
+    def parameter_change(self):
+        self.kernel.parameter_change()
+        self._fill_values()
+
+    def _fill_values(self):
+        from . import engine
+        from .preblur import get_preblur
+        self._drop_svd()
+        self._B = get_preblur(self.omega, self._b)
+        dB = np.asarray(self.omega.delta)[:, None] * self._B
+        self._K = engine.matmul_host(np.asarray(self.kernel.K, dtype=np.float64), dB)       # device GEMM
+        self._K_delta = self.kernel.K_delta
+
+    def transform(self, T):
+        self.kernel.transform(T)
+        self._fill_values()
+        self._T = self.kernel._T
+
+    def get_omega(self):
+        return self.kernel.omega
+
+    def set_omega(self, omega):
+        self.kernel.omega = omega
+
+    omega = property(get_omega, set_omega)
+
+    @property
+    def b(self):
+        return self._b
+
+    @property
+    def data_variable(self):
+        return self.kernel.data_variable
+
+    @data_variable.setter
+    def data_variable(self, value):
+        self.kernel.data_variable = value

@@ -20,7 +20,7 @@ import numpy as np
 from .alpha_meshes import LogAlphaMesh
 from .analyzers import (LineFitAnalyzer, Chi2CurvatureAnalyzer, EntropyAnalyzer, BryanAnalyzer, ClassicAnalyzer)
 from .cost_functions import MaxEntCostFunction, BryanCostFunction
-from .functions import PlusMinusEntropy, PlusMinusH_of_v
+from .functions import PlusMinusEntropy, PlusMinusH_of_v, PreblurA_of_H
 from .logtaker import Logtaker, VerbosityFlags
 from .maxent_result import MaxEntResult
 from .minimizers import LevenbergMinimizer
@@ -119,7 +119,8 @@ class MaxEntLoop(object):
             raise NotImplementedError("only NormalLogProbability is evaluated by the fused kernel")
         self.K.reduce_singular_space(self.reduce_singular_space)
         self.check_consistency()
-        job.update(problem=self.shared_problem(variant), scale=self._scale(), omega=self.omega,
+        blur = self.A_of_H._B if isinstance(self.A_of_H, PreblurA_of_H) else None     # A = B H (functions.py:991-993)
+        job.update(problem=self.shared_problem(variant), scale=self._scale(), omega=self.omega, blur=blur,
                    D=np.array(self.D.D, dtype=np.float64),
                    G_orig=np.array(self.cost_function.G_orig, dtype=np.float64),
                    data_variable=np.array(self.data_variable, dtype=np.float64), K_delta=self.K.K_delta)
@@ -163,17 +164,22 @@ class MaxEntLoop(object):
             res = engine.run_sweep(prob, np.stack([job["G"] for job in group]), alpha_eff, probability=want_p, lm=lm,
                                    chi2_factor=self.cost_function.chi2_factor, want_A=True, want_v=True,
                                    analyze_results=False, D=D_rows)
+            H_all = (res.A * prob.delta).cpu().numpy()          # the sweep writes H / delta (IdentityA_of_H)
             host = dict(A=res.A.cpu().numpy(), v=prob.v_to_reference_basis(res.v).cpu().numpy(),
                         chi2=res.chi2.cpu().numpy(), S=res.S.cpu().numpy(), Q=res.Q.cpu().numpy(),
                         logp=res.logp.cpu().numpy(), status=res.status.cpu().numpy(), n_iter=res.n_iter.cpu().numpy())
             width = str(int(np.ceil(np.log10(max(len(alpha_eff), 1)))))
             for b, job in enumerate(group):
                 elem, cidx = job["matrix_element"], job["complex_index"]
-                A = host["A"][b]
+                A, H = host["A"][b], H_all[b]
+                if job["blur"] is not None:                  # preblur: the spectral function is the blurred hidden image
+                    import torch
+                    Bd = torch.as_tensor(np.ascontiguousarray(job["blur"]), device=res.A.device)
+                    A = ((res.A[b] * prob.delta) @ Bd.transpose(0, 1)).cpu().numpy()
                 conv = (host["status"][b] & 1).astype(bool)
                 n_iter = host["n_iter"][b]
                 record = dict(alpha=alpha_eff, v=host["v"][b], chi2=host["chi2"][b], S=host["S"][b], Q=host["Q"][b],
-                              A=A, H=A * np.asarray(job["omega"].delta)[None, :],
+                              A=A, H=H,
                               probability=host["logp"][b] if want_p else np.full(len(alpha_eff), np.nan),
                               omega=job["omega"], G=job["G"], G_orig=job["G_orig"],
                               data_variable=job["data_variable"], G_rec=np.dot(A, np.asarray(job["K_delta"]).T),

@@ -25,7 +25,7 @@ GOLD = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
 
 def run_reference(tm_mod, tau, G, err, omega_pts, alpha_mesh, cost_function="normal", probability=None,
-                  reduce_singular_space=1e-14, extra_analyzers=False, noise_floor=True):
+                  reduce_singular_space=1e-14, extra_analyzers=False, noise_floor=True, preblur_b=None):
     """TauMaxEnt run through the reference's public API (python/tau_maxent.py)."""
     m = tm_mod
     kw = dict(cost_function=cost_function, probability=probability,
@@ -36,6 +36,9 @@ def run_reference(tm_mod, tau, G, err, omega_pts, alpha_mesh, cost_function="nor
     tm.omega = m.DataOmegaMesh(np.array(omega_pts))
     tm.alpha_mesh = m.DataAlphaMesh(np.array(alpha_mesh))
     tm.set_error(err)
+    if preblur_b is not None:            # doc/guide/preblur_example.py:46-52
+        tm.A_of_H = m.PreblurA_of_H(b=preblur_b, omega=tm.omega)
+        tm.K = m.PreblurKernel(K=tm.K, b=preblur_b)
     t0 = time.time()
     res = tm.run()
     wall = time.time() - t0
@@ -62,6 +65,9 @@ def run_reference(tm_mod, tau, G, err, omega_pts, alpha_mesh, cost_function="nor
         tm2.omega = m.DataOmegaMesh(np.array(omega_pts))
         tm2.alpha_mesh = m.DataAlphaMesh(np.array(alpha_mesh))
         tm2.set_error(err)
+        if preblur_b is not None:
+            tm2.A_of_H = m.PreblurA_of_H(b=preblur_b, omega=tm2.omega)
+            tm2.K = m.PreblurKernel(K=tm2.K, b=preblur_b)
         res2 = tm2.run()
         A1, A2 = np.array(res.A), np.array(res2.A)
         out["noise_A"] = np.max(np.abs(A1 - A2), axis=1) / np.max(np.abs(A1), axis=1)
@@ -161,7 +167,22 @@ def main():
                 out["ref_idx_LineFitAnalyzer_%d%d" % (i, j)] = int(ar["LineFitAnalyzer"]["alpha_index"])
     np.savez_compressed(os.path.join(GOLD, "g6_elementwise_2x2.npz"), **out)
     print("g6 done")
+    preblur_case(m)
+
+
+def preblur_case(m):
+    """G7: preblur formalism (PreblurKernel + PreblurA_of_H, b = 0.3) on the G2 data."""
+    tau, G, om = synthetic(200, 100)
+    amesh = m.LogAlphaMesh(0.05, 2000, 14)
+    out, tm, res = run_reference(m, tau, G, 1.e-4, om, amesh, reduce_singular_space=1e-11, preblur_b=0.3)
+    out["preblur_b"] = 0.3
+    out["ref_G_rec_last"] = np.array(res.G_rec)[-1]
+    np.savez_compressed(os.path.join(GOLD, "g7_preblur_200x100.npz"), **out)
+    print("g7", out["ref_n_sv"], out["ref_wall"], out.get("ref_idx_LineFitAnalyzer"), out["noise_A"])
 
 
 if __name__ == "__main__":
-    main()
+    if "--preblur-only" in sys.argv:
+        preblur_case(import_reference())
+    else:
+        main()

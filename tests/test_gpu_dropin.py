@@ -385,3 +385,30 @@ def test_maxent_loop_with_data_kernel():
         for name in ('LineFitAnalyzer', 'Chi2CurvatureAnalyzer', 'EntropyAnalyzer'):
             assert res.analyzer_results[name]['alpha_index'] == o["analyzers"][name]["alpha_index"]
         np.testing.assert_allclose(res.G_rec[-1], (Kmat * om.delta[None, :]) @ res.A[-1], rtol=1e-12)
+
+
+def test_preblur_matches_reference_run():
+    """Preblur formalism (PreblurKernel + PreblurA_of_H, doc/guide/preblur_example.py:46-52):
+    the same user script as oracle/make_golden.py ran on the reference (fixture g7)."""
+    g = gc.load_golden("g7_preblur_200x100.npz")
+    b = float(g["preblur_b"])
+    tm = _tau_maxent_from_fixture(g)
+    K_tau = tm.K
+    tm.A_of_H = mb.PreblurA_of_H(b=b, omega=tm.omega)
+    tm.K = mb.PreblurKernel(K=K_tau, b=b)
+    res = tm.run()
+    assert len(tm.K.S) == int(g["ref_n_sv"])
+    np.testing.assert_allclose(tm.K.K, K_tau.K @ (tm.omega.delta[:, None] * mb.get_preblur(tm.omega, b)), rtol=1e-12, atol=1e-300)
+    gc.check_against_reference(g, _ResView(res), rtol_chi2_S=2e-7)
+    # the hidden image itself is only determined up to the near-null space of the blur: compare it where the
+    # problem is well determined (large alpha), A = B H everywhere (done above)
+    dH = gc.rel_A(res.H, g["ref_H"])
+    assert np.all(dH[:9] <= 1e-8), dH
+    np.testing.assert_allclose(res.A, res.H @ mb.get_preblur(tm.omega, b).T, rtol=1e-12, atol=1e-300)    # A = B H
+    np.testing.assert_allclose(res.G_rec[-1], g["ref_G_rec_last"], rtol=0, atol=1e-8)
+    # switching the blur off again gives the plain result
+    tm.A_of_H = mb.IdentityA_of_H(tm.omega)
+    tm.K = K_tau
+    r0 = tm.run()
+    np.testing.assert_allclose(r0.H, r0.A * tm.omega.delta[None, :], rtol=1e-15)
+    assert not np.allclose(r0.A[5], res.A[5], rtol=1e-3)

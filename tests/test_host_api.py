@@ -93,9 +93,17 @@ def test_cost_function_variants():
                                                                                    H_of_v=mb.PlusMinusH_of_v())):
         with pytest.raises(NotImplementedError):
             bad.variant()
-    for cls in (mb.ComplexChi2, mb.NoExpH_of_v, mb.PreblurA_of_H, mb.IOmegaKernel, mb.PreblurKernel):
+    for cls in (mb.ComplexChi2, mb.NoExpH_of_v, mb.IOmegaKernel):
         with pytest.raises(NotImplementedError):
             cls()
+    om = mb.HyperbolicOmegaMesh(-5, 5, 40)
+    pre = mb.PreblurA_of_H(b=0.3, omega=om)
+    assert mb.MaxEntCostFunction(A_of_H=pre).variant() == "normal"
+    B = mb.get_preblur(om, 0.3)
+    np.testing.assert_allclose(B @ om.delta, np.ones(40), rtol=1e-12)            # exact after the second normalisation
+    np.testing.assert_allclose((om.delta @ B)[5:-5], np.ones(30), rtol=1e-2)     # approximate for the first
+    pre.b = 0.5
+    assert not np.allclose(pre._B, B)
     with pytest.raises(NotImplementedError):
         mb.MaxEntCostFunction()(np.zeros(3))                # no host evaluation of Q(v)
 
