@@ -225,11 +225,9 @@ def run_native(a):
     sampler = ClockSampler(local)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sweep_ms = 0.0
     ev0.record()
     for _ in range(a.steps):
         res = job.run_device(G_dev)
-        sweep_ms += 0.0
     ev1.record()
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
