@@ -105,9 +105,9 @@ def test_small_random_batch_vs_oracle(torch_cuda, variant):
     D = mo.flat_default_model(pr["omega"])
     mesh = mo.log_alpha_mesh(0.05, 500, 10)
     prob = engine.SharedProblem(pr["K"], err, D, pr["delta"], variant=variant, reduce_singular_space=1e-10)
-    res = engine.run_sweep(prob, G, mesh * n_tau, probability=(variant == "normal"))
+    res = engine.run_sweep(prob, G, mesh * n_tau, probability=True)
     for b in range(G.shape[0]):
-        o = mo.maxent_loop(pr["K"], G[b], err, pr["omega"], mesh, variant=variant, probability=(variant == "normal"),
+        o = mo.maxent_loop(pr["K"], G[b], err, pr["omega"], mesh, variant=variant, probability=True,
                            reduce_singular_space=1e-10)
         o2 = mo.maxent_loop(pr["K"], G[b] * (1 + 1e-15), err, pr["omega"], mesh, variant=variant,
                             reduce_singular_space=1e-10, analyzers=False)
@@ -121,10 +121,10 @@ def test_small_random_batch_vs_oracle(torch_cuda, variant):
         idx = res.alpha_index[b].cpu().numpy()
         for slot, name in enumerate(gc.AN_NAMES[:3]):
             assert idx[slot] == o["analyzers"][name]["alpha_index"], (variant, b, name)
-        if variant == "normal":
-            p = res.logp[b].cpu().numpy()
-            assert np.all(np.abs(p - o["probability"]) <= 1e-6 * np.abs(o["probability"]))
-            assert idx[3] == o["analyzers"]["ClassicAnalyzer"]["alpha_index"]
+        # NormalLogProbability for every variant (plus-minus: 1/H -> 1/(H+ + H-), python/functions.py:560-564)
+        p = res.logp[b].cpu().numpy()
+        assert np.all(np.abs(p - o["probability"]) <= 1e-6 * np.abs(o["probability"])), (variant, b, p, o["probability"])
+        assert idx[3] == o["analyzers"]["ClassicAnalyzer"]["alpha_index"]
 
 
 def test_maxiter_flags_not_converged(torch_cuda):
