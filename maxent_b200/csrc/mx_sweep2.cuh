@@ -1202,6 +1202,7 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                     double u_mu = uvalid ? ctl.umu[lane] : 0.0;
                     double u_Q = uvalid ? ctl.uQ[lane] : 0.0;
                     int u_fail = uvalid ? ctl.ufail[lane] : 0;
+                    __syncwarp();         // every lane has its copy of the control block before any lane updates it below
                     // two dampings are equivalent when they give bitwise the same matrix J + shift(mu).  The entry
                     // with the smallest |J_kk| can only round to the same value if they differ by less than two of
                     // its ulps: cheap per-lane pre-test, the full comparison is rarely reached
