@@ -257,6 +257,22 @@ def _problem_struct(prob, alpha, probability, lm, chi2_factor, D_rows=None, v0_r
                           _ptr(v0_rows if per else prob.v0), lm.c_struct())
 
 
+def _problem_args(prob, alpha, probability, lm, chi2_factor, D_rows=None, v0_rows=None):
+    """The same problem description as the leading arguments of the torch operators (maxent_b200/ops.py)."""
+    per = D_rows is not None
+    dims = [prob.n_tau, prob.n_omega, prob.n_sv, int(alpha.numel()), _lib.VARIANTS[prob.variant],
+            int(bool(probability)), int(getattr(prob, "engine", 0)), int(per), int(lm.maxiter), int(lm.miniter)]
+    params = [float(chi2_factor), float(lm.mu0), float(lm.nu), float(lm.max_mu), float(lm.conv_max_derivative),
+              float(lm.conv_rel_change)]
+    return (prob.Vt, prob.Qw, prob.Q, prob.sqrtw, prob.xi, D_rows if per else prob.D, prob.delta, alpha,
+            v0_rows if per else prob.v0, dims, params)
+
+
+def _ops():
+    from . import ops
+    return ops
+
+
 def per_spectrum_models(prob, D, A_init=None):
     """Device buffers for one default model PER SPECTRUM (MxProblem.per_spectrum_model = 1): D[B, n_omega] (incl.
     delta omega, like DefaultModel.D) -> (D_rows[B, ldD], v0_rows[B, n_sv]); v0 = V'^T log(H0 / D) with
@@ -289,11 +305,9 @@ def project_data(prob, G):
         G = _dev_f64(G, dev)
         B = int(G.shape[0])
         alpha = torch.ones((1,), dtype=torch.float64, device=dev)
-        p = _problem_struct(prob, alpha, False, LMParams(), 1.0)
         gt = torch.empty((B, prob.n_sv), dtype=torch.float64, device=dev)
         c0 = torch.empty((B,), dtype=torch.float64, device=dev)
-        _lib.check(prob.lib.mx_project_data(ctypes.byref(p), _ptr(G), B, _ptr(gt), _ptr(c0), _stream(dev)),
-                   "mx_project_data")
+        _ops().project_data(*_problem_args(prob, alpha, False, LMParams(), 1.0), G, gt, c0)
     return gt, c0
 
 
@@ -316,9 +330,8 @@ def analyze(alpha, chi2, S, logp, A, gamma=0.2, linefit_deg=0, bryan_by_integrat
         idx = torch.full((B, _lib.N_ANALYZERS), -1, dtype=torch.int32, device=dev)
         A_out = torch.empty((B, _lib.N_ANALYZERS, n_omega), dtype=torch.float64, device=dev) if A is not None else None
         aux = torch.empty((B, 4 + 2 * n_alpha), dtype=torch.float64, device=dev) if want_aux else None
-        _lib.check(lib.mx_analyze(_ptr(alpha), _ptr(chi2), _ptr(S), _ptr(logp), _ptr(A), B, n_alpha, n_omega,
-                                  float(gamma), int(linefit_deg), int(bool(bryan_by_integration)),
-                                  _ptr(idx), _ptr(A_out), _ptr(aux), _stream(dev)), "mx_analyze")
+        _ops().analyze(alpha, chi2, S, logp, A, float(gamma), int(linefit_deg), bool(bryan_by_integration),
+                       idx, A_out, aux)
     if want_aux:
         return idx, A_out, aux
     return idx, A_out
@@ -350,10 +363,12 @@ def run_sweep(prob, G, alpha_eff, probability=False, lm=None, chi2_factor=1.0, w
             D_rows, v0_rows = per_spectrum_models(prob, D, getattr(prob, "A_init_host", None))
             if D_rows.shape[0] != B:
                 raise ValueError("D has %d rows for %d spectra" % (D_rows.shape[0], B))
+        ops = _ops()
         p = _problem_struct(prob, alpha, probability, lm, chi2_factor, D_rows, v0_rows)
+        pargs = _problem_args(prob, alpha, probability, lm, chi2_factor, D_rows, v0_rows)
         gt = torch.empty((B, s), dtype=f64, device=dev)
         c0 = torch.empty((B,), dtype=f64, device=dev)
-        _lib.check(lib.mx_project_data(ctypes.byref(p), _ptr(G), B, _ptr(gt), _ptr(c0), stream), "mx_project_data")
+        ops.project_data(*pargs, G, gt, c0)
         r = SweepResult()
         r.alpha = alpha
         r.n_sv = s
@@ -376,14 +391,11 @@ def run_sweep(prob, G, alpha_eff, probability=False, lm=None, chi2_factor=1.0, w
         ws = getattr(prob, "_workspace", None)
         if ws is None or ws.numel() < ws_bytes:
             ws = prob._workspace = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-        out = _lib.MxSweepOut(_ptr(r.v), _ptr(r.A), _ptr(r.chi2), _ptr(r.S), _ptr(r.Q), _ptr(r.logp),
-                              _ptr(r.n_iter), _ptr(r.n_qeval), _ptr(r.n_solve), _ptr(r.status),
-                              _ptr(r.n_trial), _ptr(r.n_batch), _ptr(r.phase_cycles))
         if time_kernel:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-        _lib.check(lib.mx_alpha_sweep(ctypes.byref(p), _ptr(gt), _ptr(c0), B, ctypes.byref(out), _ptr(ws), ws_bytes,
-                                      stream), "mx_alpha_sweep")
+        ops.alpha_sweep(*pargs, gt, c0, r.v, r.A, r.chi2, r.S, r.Q, r.logp, r.n_iter, r.n_qeval, r.n_solve, r.status,
+                        r.n_trial, r.n_batch, r.phase_cycles, ws)
         if time_kernel:
             ev1.record()
             ev1.synchronize()
@@ -392,8 +404,6 @@ def run_sweep(prob, G, alpha_eff, probability=False, lm=None, chi2_factor=1.0, w
         if analyze_results:
             r.alpha_index = torch.full((B, _lib.N_ANALYZERS), -1, dtype=i32, device=dev)
             r.A_out = torch.empty((B, _lib.N_ANALYZERS, n_omega), dtype=f64, device=dev) if want_A else None
-            _lib.check(lib.mx_analyze(_ptr(alpha), _ptr(r.chi2), _ptr(r.S), _ptr(r.logp) if probability else None,
-                                      _ptr(r.A), B, n_alpha, n_omega, float(gamma), int(linefit_deg),
-                                      int(bool(bryan_by_integration)), _ptr(r.alpha_index), _ptr(r.A_out), None, stream),
-                       "mx_analyze")
+            ops.analyze(alpha, r.chi2, r.S, r.logp if probability else None, r.A, float(gamma), int(linefit_deg),
+                        bool(bryan_by_integration), r.alpha_index, r.A_out, None)
         return r

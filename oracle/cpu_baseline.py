@@ -28,9 +28,20 @@ from oracle import maxent_oracle as mo  # noqa: E402
 _P = {}
 
 
+def kresolved_inputs(n_tau, n_omega, kpoints, rows, seed=3):
+    """The k-resolved batch (SURVEY.md 8(d) C3 recipe = BASELINE config 3): spectrum k of `kpoints` is a Gaussian at
+    mu_k = 2 cos(2 pi k / kpoints) with noise row k of default_rng(seed).standard_normal((kpoints, n_tau));
+    `rows` selects the k values."""
+    rows = np.asarray(rows, dtype=int)
+    noise = np.random.default_rng(seed).standard_normal((kpoints, n_tau))[rows]
+    return mo.synthetic_problem(n_tau, n_omega, mu=2.0 * np.cos(2.0 * np.pi * rows / kpoints), noise=noise)
+
+
 def bench_inputs(n_tau, n_omega, n_spectra, seed=5, first=0):
     """The benchmark's synthetic batch (SURVEY.md 8(d) C5 recipe): rows of
     default_rng(seed).standard_normal((B, n_tau)) as noise on a Gaussian A(omega), mu = 1."""
+    if _P.get("krows") is not None:
+        return kresolved_inputs(n_tau, n_omega, _P["kpoints"], _P["krows"])
     rng = np.random.default_rng(seed)
     noise = rng.standard_normal((first + n_spectra, n_tau))[first:]
     return mo.synthetic_problem(n_tau, n_omega, mu=np.ones(n_spectra), noise=noise)
@@ -57,11 +68,14 @@ def _one(b):
                 linefit=int(an["LineFitAnalyzer"]["alpha_index"]), chi2curv=int(an["Chi2CurvatureAnalyzer"]["alpha_index"]))
 
 
-def run(n_tau, n_omega, n_alpha, spectra, procs, thr=1e-11, seed=5, dump=None):
+def run(n_tau, n_omega, n_alpha, spectra, procs, thr=1e-11, seed=5, dump=None, kpoints=0, krows=None):
     import multiprocessing as mp
     ctx = mp.get_context("fork")
     t0 = time.perf_counter()
     _P["keep"] = dump is not None            # inherited by the forked workers
+    _P["kpoints"], _P["krows"] = kpoints, (None if not kpoints else list(krows))
+    if kpoints:
+        spectra = len(krows)
     if procs <= 1:
         _init(n_tau, n_omega, n_alpha, spectra, thr, seed)
         rows = [_one(b) for b in range(spectra)]
@@ -92,10 +106,14 @@ def main():
     ap.add_argument("--procs", type=int, default=0)
     ap.add_argument("--thr", type=float, default=1e-11)
     ap.add_argument("--dump", default=None, help="write the oracle's A/chi2/S/Q/picks of the sample to this .npz")
+    ap.add_argument("--kpoints", type=int, default=0, help="k-resolved recipe (C3): size of the k mesh")
+    ap.add_argument("--krows", default="", help="comma-separated k values to run (with --kpoints)")
     a = ap.parse_args()
     procs = a.procs or (os.cpu_count() or 1)
     spectra = a.spectra or procs
-    print(json.dumps(run(a.n_tau, a.n_omega, a.n_alpha, spectra, procs, a.thr, dump=a.dump)))
+    krows = [int(x) for x in a.krows.split(",") if x]
+    print(json.dumps(run(a.n_tau, a.n_omega, a.n_alpha, spectra, procs, a.thr, dump=a.dump, kpoints=a.kpoints,
+                         krows=krows)))
 
 
 if __name__ == "__main__":

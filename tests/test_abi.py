@@ -100,3 +100,20 @@ def test_missing_library_is_loud(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libmaxent_b200.so")
     with pytest.raises(_lib.MaxEntLibraryError):
         _lib.load()
+
+
+def test_torch_operators_registered_cuda_only():
+    """The hot path is driven through torch.ops.maxent_b200.* (maxent_b200/ops.py): the three operators exist with
+    caller-allocated outputs, and there is no CPU kernel behind them -- host tensors are refused by the dispatcher."""
+    import torch
+    from maxent_b200 import ops
+    for name in ops.OPERATORS:
+        schema = str(getattr(torch.ops.maxent_b200, name).default._schema)
+        assert "(a!)" in schema and schema.endswith("-> ()"), schema
+    t = torch.zeros((1, 4), dtype=torch.float64)
+    with pytest.raises(NotImplementedError):
+        ops.analyze(t[0], t, t, None, None, 0.2, 0, False, torch.zeros((1, 5), dtype=torch.int32), None, None)
+    z = torch.zeros(4, dtype=torch.float64)
+    with pytest.raises(NotImplementedError):
+        ops.project_data(z, z, z, z, z, z, z, z, z, [2, 2, 2, 1, 0, 0, 0, 0, 10, 0], [1.0, 1e-18, 1.3, 1e20, 1e-4, 1e-16],
+                         t, t, z)
