@@ -318,6 +318,7 @@ def run_native(a):
                          "kernel_share_of_step": kernel_ms / (dev_ms / a.steps),
                          "flops_per_launch": flops, "flops_per_spectrum": flops / B,
                          "flops_survey_formula_per_spectrum": flops_survey / B,
+                         "frac_with_survey_formula": flops_survey / (kernel_ms * 1e-3) / 1e12 / peak,
                          "pipe": "FP64 (DMMA m8n8k4 + DFMA share one pipe on B200)", "peak_source": peak_src},
         }
         if world == 1 and not a.no_cpu_baseline:

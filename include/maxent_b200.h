@@ -50,7 +50,8 @@ extern "C" {
 #define MX_STATUS_SKIPPED    2   /* max|G| < G_threshold (maxent_loop.py:174-179) */
 
 /* Levenberg-Marquardt parameters = LevenbergMinimizer.__init__ (levenberg_minimizer.py:92-121)
- * with the default convergence MaxDerivative(1e-4) | RelativeFunctionChange(1e-16). */
+ * with the default convergence MaxDerivative(1e-4) | RelativeFunctionChange(1e-16); a criterion is switched off
+ * by a negative threshold.  J_squared is not available. */
 typedef struct {
     int32_t maxiter;          /* 1000  */
     int32_t miniter;          /* 0     */
@@ -59,6 +60,9 @@ typedef struct {
     double  max_mu;           /* 1e20  */
     double  conv_max_derivative;   /* 1e-4  */
     double  conv_rel_change;       /* 1e-16 */
+    double  conv_abs_change;       /* -1 (off): FunctionChangeConvergenceMethod, |Q0 - Q1| < x (convergence_methods.py:100-110) */
+    int32_t marquardt;             /* 0: J + mu 1 ; 1: J + mu diag(J)   (levenberg_minimizer.py:181-185) */
+    int32_t reserved;              /* 0 */
 } MxLMParams;
 
 /* Problem state shared by every spectrum of a batch (built once per kernel/err by

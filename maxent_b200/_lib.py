@@ -29,7 +29,8 @@ class MaxEntLibraryError(RuntimeError):
 class MxLMParams(ctypes.Structure):
     _fields_ = [("maxiter", ctypes.c_int32), ("miniter", ctypes.c_int32), ("mu0", ctypes.c_double),
                 ("nu", ctypes.c_double), ("max_mu", ctypes.c_double),
-                ("conv_max_derivative", ctypes.c_double), ("conv_rel_change", ctypes.c_double)]
+                ("conv_max_derivative", ctypes.c_double), ("conv_rel_change", ctypes.c_double),
+                ("conv_abs_change", ctypes.c_double), ("marquardt", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class MxProblem(ctypes.Structure):

@@ -292,6 +292,7 @@ static int fill_args(const MxProblem* p, SweepArgs& a) {
     a.maxiter = p->lm.maxiter; a.miniter = p->lm.miniter;
     a.mu0 = p->lm.mu0; a.nu = p->lm.nu; a.max_mu = p->lm.max_mu;
     a.conv_maxd = p->lm.conv_max_derivative; a.conv_relq = p->lm.conv_rel_change; a.eta = p->chi2_factor;
+    a.conv_absq = p->lm.conv_abs_change; a.marquardt = p->lm.marquardt ? 1 : 0;
     a.per_spec = p->per_spectrum_model ? 1 : 0;
     a.Vt = p->Vt; a.D = p->D; a.delta = p->delta; a.xi = p->xi; a.alpha = p->alpha; a.v0 = p->v0;
     return MX_OK;
@@ -302,6 +303,7 @@ int mx_sweep_config(int32_t n_sv, int32_t engine, int32_t* engine_used, int32_t*
     SweepArgs a = {};
     a.n_sv = n_sv;
     a.B = 1;
+    a.conv_absq = -1.0;
     int t = 0, sm = 0, eng = 0;
     const int rc = dispatch_sweep(a, nullptr, true, engine, &eng, &t, &sm, nullptr);
     if (rc != MX_OK) return rc;
@@ -319,6 +321,9 @@ int64_t mx_sweep_workspace_bytes(const MxProblem* p, int32_t B) {
     SweepArgs a = {};
     a.n_sv = p->n_sv;
     a.B = B > 0 ? B : 1;
+    a.per_spec = p->per_spectrum_model ? 1 : 0;
+    a.marquardt = p->lm.marquardt ? 1 : 0;
+    a.conv_absq = p->lm.conv_abs_change;
     int eng = 0, grid = 0;
     const int rc = dispatch_sweep(a, nullptr, true, p->engine, &eng, nullptr, nullptr, &grid);
     if (rc != MX_OK) return rc;

@@ -34,7 +34,7 @@ int dispatch_sweep(SweepArgs& a, cudaStream_t stream, bool query, int engine, in
     const int nt = (s + 7) / 8;
     if (nt > 10) return MX_ERR_UNSUPPORTED;
     if (engine == 0) engine = 2;
-    if (engine == 1 && (nt > 8 || a.per_spec)) return MX_ERR_UNSUPPORTED;
+    if (engine == 1 && (nt > 8 || a.per_spec || a.marquardt || a.conv_absq >= 0.0)) return MX_ERR_UNSUPPORTED;
     if (o_engine) *o_engine = engine;
     if (engine == 2) {
         if (o_t) *o_t = 1;

@@ -953,7 +953,13 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
         __syncthreads();
     };
 
-    auto shift_of = [&](int i, double mu) -> double { return bryan ? mu / sm[LY::o_lam + i] : mu; };
+    // damping of diagonal entry i: mu * 1 (Bryan: the system is divided by Lambda), or -- Marquardt's variant,
+    // levenberg_minimizer.py:181-185 -- mu * diag(J): J_ii + mu * J_ii, which for Bryan is again row i of
+    // (eta Lambda Z + mu diag(eta Lambda Z)) divided by Lambda_i
+    const bool marq = a.marquardt != 0;
+    auto shift_of = [&](int i, double mu) -> double {
+        return marq ? mu * sm[LY::o_jd + i] : (bryan ? mu / sm[LY::o_lam + i] : mu);
+    };
 
     // ---- P3: factorise J + shift(mu_u) and solve for every unique trial (one solver warp per matrix) -------
     auto solve_trials = [&]() {
@@ -1124,7 +1130,9 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                     LM& L = ctl.lm;
                     L.Q1 = 0.5 * ctl.chi2_cur * a.eta - ctl.alpha * ctl.S_cur;
                     // MaxDerivative(1e-4) | RelativeFunctionChange(1e-16)   (levenberg_minimizer.py:103-106)
-                    const bool conv = (ctl.maxf < a.conv_maxd) || (fabs(fabs(L.Q0 - L.Q1) / L.Q1) < a.conv_relq);
+                    //   | FunctionChange(x) when asked for (convergence_methods.py:100-110)
+                    const bool conv = (ctl.maxf < a.conv_maxd) || (fabs(fabs(L.Q0 - L.Q1) / L.Q1) < a.conv_relq) ||
+                                      (fabs(L.Q0 - L.Q1) < a.conv_absq);
                     ctl.conv = conv ? 1 : 0;
                     ctl.action = ((conv && ctl.it >= a.miniter) || ctl.it >= a.maxiter) ? 1 : 0;
                 }
@@ -1207,7 +1215,7 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                     // with the smallest |J_kk| can only round to the same value if they differ by less than two of
                     // its ulps: cheap per-lane pre-test, the full comparison is rarely reached
                     auto maybe = [&](double ma, double mb) -> bool {
-                        return ma == mb || bryan || !(fabs(ma - mb) > 4.5e-16 * (jdmin + fmax(ma, mb)));
+                        return ma == mb || bryan || marq || !(fabs(ma - mb) > 4.5e-16 * (jdmin + fmax(ma, mb)));
                     };
                     auto equiv_full = [&](double ma, double mb) -> bool {
                         if (ma == mb) return true;
@@ -1320,7 +1328,7 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                         // everything on real values and re-plans when an entry is missing -- so a fast path can cost
                         // speculation efficiency but never change a result.
                         bool fast = false;
-                        if (!bryan) {
+                        if (!bryan && !marq) {
                             const double nu = a.nu, inu = 1.0 / a.nu;
                             auto add_unique = [&](double mu) {
                                 if (lane == np) { p_mu = mu; p_slot = npu; }

@@ -29,15 +29,17 @@ class LMParams(object):
     """LevenbergMinimizer parameters (python/minimizers/levenberg_minimizer.py:92-121)."""
 
     def __init__(self, maxiter=1000, miniter=0, mu0=1.e-18, nu=1.3, max_mu=1.e20,
-                 conv_max_derivative=1.e-4, conv_rel_change=1.e-16):
+                 conv_max_derivative=1.e-4, conv_rel_change=1.e-16, conv_abs_change=-1.0, marquardt=False):
         if nu <= 1.0:
             raise Exception('If nu <= 1, there will be an infinite loop.')   # levenberg_minimizer.py:139-140
         self.maxiter, self.miniter, self.mu0, self.nu, self.max_mu = maxiter, miniter, mu0, nu, max_mu
         self.conv_max_derivative, self.conv_rel_change = conv_max_derivative, conv_rel_change
+        self.conv_abs_change, self.marquardt = conv_abs_change, bool(marquardt)
 
     def c_struct(self):
         return _lib.MxLMParams(int(self.maxiter), int(self.miniter), float(self.mu0), float(self.nu),
-                               float(self.max_mu), float(self.conv_max_derivative), float(self.conv_rel_change))
+                               float(self.max_mu), float(self.conv_max_derivative), float(self.conv_rel_change),
+                               float(self.conv_abs_change), int(self.marquardt), 0)
 
 
 class SharedProblem(object):
@@ -261,9 +263,10 @@ def _problem_args(prob, alpha, probability, lm, chi2_factor, D_rows=None, v0_row
     """The same problem description as the leading arguments of the torch operators (maxent_b200/ops.py)."""
     per = D_rows is not None
     dims = [prob.n_tau, prob.n_omega, prob.n_sv, int(alpha.numel()), _lib.VARIANTS[prob.variant],
-            int(bool(probability)), int(getattr(prob, "engine", 0)), int(per), int(lm.maxiter), int(lm.miniter)]
+            int(bool(probability)), int(getattr(prob, "engine", 0)), int(per), int(lm.maxiter), int(lm.miniter),
+            int(lm.marquardt)]
     params = [float(chi2_factor), float(lm.mu0), float(lm.nu), float(lm.max_mu), float(lm.conv_max_derivative),
-              float(lm.conv_rel_change)]
+              float(lm.conv_rel_change), float(lm.conv_abs_change)]
     return (prob.Vt, prob.Qw, prob.Q, prob.sqrtw, prob.xi, D_rows if per else prob.D, prob.delta, alpha,
             v0_rows if per else prob.v0, dims, params)
 

@@ -8,8 +8,11 @@ holds the user-facing objects with the reference's constructor arguments and tra
 
     max|dQ/dv| < conv_max_derivative   OR   | |Q0 - Q1| / Q1 | < conv_rel_change
 
+    OR   |Q0 - Q1| < conv_abs_change
+
 so any and/or tree over ``MaxDerivativeConvergenceMethod`` / ``RelativeFunctionChangeConvergenceMethod`` /
-``NullConvergenceMethod`` maps onto it (the reference's ``&`` is an ``or`` too -- convergence_methods.py:61)."""
+``FunctionChangeConvergenceMethod`` / ``NullConvergenceMethod`` maps onto it (the reference's ``&`` is an ``or``
+too -- convergence_methods.py:61).  A negative threshold switches a criterion off."""
 import numpy as np
 
 
@@ -26,7 +29,7 @@ class ConvergenceMethod(object):
         raise NotImplementedError('Convergence is tested on the device; see thresholds()')
 
     def thresholds(self):
-        """(conv_max_derivative, conv_rel_change) for the device test; -1 disables a criterion."""
+        """(conv_max_derivative, conv_rel_change, conv_abs_change) for the device test; -1 disables a criterion."""
         raise NotImplementedError('Please use a subclass of ConvergenceMethod.')
 
 
@@ -36,7 +39,7 @@ class _Pair(ConvergenceMethod):
 
     def thresholds(self):
         a, b = self.one.thresholds(), self.two.thresholds()
-        return max(a[0], b[0]), max(a[1], b[1])          # both conjunctions accept when EITHER side does
+        return tuple(max(x, y) for x, y in zip(a, b))    # both conjunctions accept when EITHER side does
 
 
 class AndConvergenceMethod(_Pair):
@@ -52,7 +55,7 @@ class MaxDerivativeConvergenceMethod(ConvergenceMethod):
         self.convergence_criterion = convergence_criterion
 
     def thresholds(self):
-        return float(self.convergence_criterion), -1.0
+        return float(self.convergence_criterion), -1.0, -1.0
 
 
 class RelativeFunctionChangeConvergenceMethod(ConvergenceMethod):
@@ -60,14 +63,14 @@ class RelativeFunctionChangeConvergenceMethod(ConvergenceMethod):
         self.convergence_criterion = convergence_criterion
 
     def thresholds(self):
-        return -1.0, float(self.convergence_criterion)
+        return -1.0, float(self.convergence_criterion), -1.0
 
 
 class NullConvergenceMethod(ConvergenceMethod):
     """Everything counts as converged."""
 
     def thresholds(self):
-        return float(np.inf), -1.0
+        return float(np.inf), -1.0, -1.0
 
 
 class FunctionChangeConvergenceMethod(ConvergenceMethod):
@@ -75,8 +78,7 @@ class FunctionChangeConvergenceMethod(ConvergenceMethod):
         self.convergence_criterion = convergence_criterion
 
     def thresholds(self):
-        raise NotImplementedError("the absolute function-change criterion is not evaluated by the fused kernel; "
-                                  "use RelativeFunctionChangeConvergenceMethod")
+        return -1.0, -1.0, float(self.convergence_criterion)
 
 
 class Minimizer(object):
@@ -86,7 +88,8 @@ class Minimizer(object):
 
 class LevenbergMinimizer(Minimizer):
     """Parameters of the reference's LevenbergMinimizer (python/minimizers/levenberg_minimizer.py:92-121).
-    ``J_squared`` and ``marquardt`` (off by default) are not implemented by the fused kernel."""
+    ``marquardt=True`` damps with mu * diag(J) instead of mu * 1 (:181-185); ``J_squared`` (off by default) is not
+    implemented by the fused kernel."""
 
     def __init__(self, convergence=None, maxiter=1000, miniter=0, J_squared=False, marquardt=False,
                  mu0=1.e-18, nu=1.3, max_mu=1.e20, verbose_callback=None):
@@ -104,11 +107,11 @@ class LevenbergMinimizer(Minimizer):
     def lm_params(self):
         """-> engine.LMParams for the C ABI."""
         from .engine import LMParams
-        if self.J_squared or self.marquardt:
-            raise NotImplementedError("LevenbergMinimizer(J_squared / marquardt) is not on the fused path")
-        cd, cr = self.convergence.thresholds()
+        if self.J_squared:
+            raise NotImplementedError("LevenbergMinimizer(J_squared=True) is not on the fused path")
+        cd, cr, ca = self.convergence.thresholds()
         return LMParams(maxiter=self.maxiter, miniter=self.miniter, mu0=self.mu0, nu=self.nu, max_mu=self.max_mu,
-                        conv_max_derivative=cd, conv_rel_change=cr)
+                        conv_max_derivative=cd, conv_rel_change=cr, conv_abs_change=ca, marquardt=self.marquardt)
 
     def minimize(self, function, v0):
         raise NotImplementedError("LevenbergMinimizer.minimize runs inside the fused device kernel (MaxEntLoop.run); "

@@ -25,11 +25,14 @@ GOLD = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
 
 def run_reference(tm_mod, tau, G, err, omega_pts, alpha_mesh, cost_function="normal", probability=None,
-                  reduce_singular_space=1e-14, extra_analyzers=False, noise_floor=True, preblur_b=None):
+                  reduce_singular_space=1e-14, extra_analyzers=False, noise_floor=True, preblur_b=None,
+                  make_minimizer=None):
     """TauMaxEnt run through the reference's public API (python/tau_maxent.py)."""
     m = tm_mod
     kw = dict(cost_function=cost_function, probability=probability,
               reduce_singular_space=reduce_singular_space)
+    if make_minimizer is not None:
+        kw["minimizer"] = make_minimizer()
     tm = m.TauMaxEnt(**kw)
     tm.set_verbosity(m.VerbosityFlags.Quiet)
     tm.set_G_tau_data(np.array(tau), np.array(G))
@@ -59,6 +62,8 @@ def run_reference(tm_mod, tau, G, err, omega_pts, alpha_mesh, cost_function="nor
     if noise_floor:
         # The reference's own reproducibility (SURVEY.md section 0.4 / 8(c) tier T4): re-run it with
         # G * (1 + 1e-15) and record, per alpha, how far its A / chi2 / S move.
+        if make_minimizer is not None:
+            kw["minimizer"] = make_minimizer()
         tm2 = m.TauMaxEnt(**kw)
         tm2.set_verbosity(m.VerbosityFlags.Quiet)
         tm2.set_G_tau_data(np.array(tau), np.array(G) * (1.0 + 1.e-15))
@@ -168,6 +173,7 @@ def main():
     np.savez_compressed(os.path.join(GOLD, "g6_elementwise_2x2.npz"), **out)
     print("g6 done")
     preblur_case(m)
+    marquardt_case(m)
 
 
 def preblur_case(m):
@@ -181,8 +187,24 @@ def preblur_case(m):
     print("g7", out["ref_n_sv"], out["ref_wall"], out.get("ref_idx_LineFitAnalyzer"), out["noise_A"])
 
 
+def marquardt_case(m):
+    """G8: LevenbergMinimizer(marquardt=True) with MaxDerivative(1e-4) | FunctionChange(1e-9) on the G2 data
+    (python/minimizers/levenberg_minimizer.py:181-185, convergence_methods.py:100-110)."""
+    tau, G, om = synthetic(200, 100)
+    amesh = m.LogAlphaMesh(0.01, 2000, 20)
+    mk = lambda: m.LevenbergMinimizer(marquardt=True, convergence=m.OrConvergenceMethod(
+        m.MaxDerivativeConvergenceMethod(1.e-4), m.FunctionChangeConvergenceMethod(1.e-9)))
+    out, tm, res = run_reference(m, tau, G, 1.e-4, om, amesh, reduce_singular_space=1e-11, make_minimizer=mk)
+    out["lm_marquardt"] = True
+    out["lm_abs_change"] = 1.e-9
+    np.savez_compressed(os.path.join(GOLD, "g8_marquardt_200x100.npz"), **out)
+    print("g8", out["ref_n_sv"], out["ref_wall"], out.get("ref_idx_LineFitAnalyzer"), out["noise_A"])
+
+
 if __name__ == "__main__":
-    if "--preblur-only" in sys.argv:
+    if "--marquardt-only" in sys.argv:
+        marquardt_case(import_reference())
+    elif "--preblur-only" in sys.argv:
         preblur_case(import_reference())
     else:
         main()

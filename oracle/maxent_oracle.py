@@ -300,10 +300,10 @@ class BoundQ(object):
 # --------------------------------------------------------------------------------------------
 
 def levenberg_minimize(prob, alpha, v, maxiter=1000, miniter=0, mu0=1.e-18, nu=1.3, max_mu=1.e20,
-                       max_derivative=1.e-4, rel_change=1.e-16):
+                       max_derivative=1.e-4, rel_change=1.e-16, abs_change=-1.0, marquardt=False):
     """Returns (v, converged, n_iter_last).  ``v`` is updated in place like the reference (:239).
-    Convergence = MaxDerivative(1e-4) | RelativeFunctionChange(1e-16)  (:103-106,
-    python/minimizers/convergence_methods.py:64-122)."""
+    Convergence = MaxDerivative(1e-4) | RelativeFunctionChange(1e-16) [| FunctionChange(abs_change)]  (:103-106,
+    python/minimizers/convergence_methods.py:64-122); ``marquardt`` damps with diag(J) (:181-185)."""
     converged = False
     mu = mu0
     func_val = BoundQ(prob, alpha, v)
@@ -317,10 +317,11 @@ def levenberg_minimize(prob, alpha, v, maxiter=1000, miniter=0, mu0=1.e-18, nu=1
         with np.errstate(all='ignore'):
             is1 = np.max(np.abs(f)) < max_derivative
             is2 = np.abs(np.abs(Q0 - Q1) / Q1) < rel_change
-        converged = bool(is1 or is2)
+            is3 = np.abs(Q0 - Q1) < abs_change
+        converged = bool(is1 or is2 or is3)
         if converged and i >= miniter:
             break
-        Id = np.eye(len(J))
+        Id = np.diag(np.diag(J)) if marquardt else np.eye(len(J))
         Q0 = Q1
         dv = solve(J + mu * Id, f); prob.n_solve += 1
         old = np.seterr(all='ignore')
@@ -360,7 +361,7 @@ def levenberg_minimize(prob, alpha, v, maxiter=1000, miniter=0, mu0=1.e-18, nu=1
 
 def maxent_loop(K, G, err, omega, alpha_mesh, D=None, variant="normal", probability=False,
                 reduce_singular_space=1.e-14, scale_alpha="Ndata", A_init=None, G_threshold=1.e-10,
-                chi2_factor=1.0, maxiter=1000, fast_d2=False, svd=None, analyzers=True):
+                chi2_factor=1.0, maxiter=1000, fast_d2=False, svd=None, analyzers=True, lm_options=None):
     """One ``MaxEntLoop.run``.  Returns a dict of arrays (the fields of MaxEntResultData,
     python/maxent_result.py:181-188) plus counters, or None if G is below threshold (:174-179)."""
     G = np.asarray(G, dtype=float)
@@ -396,7 +397,7 @@ def maxent_loop(K, G, err, omega, alpha_mesh, D=None, variant="normal", probabil
     t0 = time.perf_counter()
     for ia, alpha in enumerate(alpha_mesh):                           # :241-266
         a_eff = alpha * scale
-        v, conv, nit = levenberg_minimize(prob, a_eff, v, maxiter=maxiter)
+        v, conv, nit = levenberg_minimize(prob, a_eff, v, maxiter=maxiter, **(lm_options or {}))
         Qmin = BoundQ(prob, a_eff, v)
         out["alpha"][ia] = a_eff
         out["chi2"][ia] = Qmin.chi2()

@@ -76,6 +76,18 @@ def test_tau_maxent_matches_reference_run(name):
     assert np.all(res.converged)
 
 
+def test_tau_maxent_marquardt_minimizer():
+    """The user-level spelling of the G8 fixture: TauMaxEnt(minimizer=LevenbergMinimizer(marquardt=True,
+    convergence=MaxDerivative(1e-4) | FunctionChange(1e-9)))."""
+    g = gc.load_golden("g8_marquardt_200x100.npz")
+    tm = _tau_maxent_from_fixture(g)
+    tm.minimizer = mb.LevenbergMinimizer(marquardt=True, convergence=mb.OrConvergenceMethod(
+        mb.MaxDerivativeConvergenceMethod(1.e-4), mb.FunctionChangeConvergenceMethod(1.e-9)))
+    res = tm.run()
+    gc.check_against_reference(g, _ResView(res), rtol_chi2_S=2e-7)
+    assert np.all(res.converged)
+
+
 def test_tau_maxent_vs_hand_assembled_loop():
     """test/python/tau_maxent.py:31-135: TauMaxEnt and a MaxEntLoop assembled from its parts give the same
     result field by field, and the probabilities are the reference's literal numbers to 6 decimals."""

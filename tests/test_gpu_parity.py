@@ -47,6 +47,24 @@ def test_golden_reference_parity(torch_cuda, name):
     assert bool((res.status[0] & 1).all()), "every alpha converged in the reference run"
 
 
+def test_marquardt_damping_and_function_change_criterion(torch_cuda):
+    """LevenbergMinimizer(marquardt=True) -- J + mu diag(J), levenberg_minimizer.py:181-185 -- with the convergence
+    MaxDerivative(1e-4) | FunctionChange(1e-9) (convergence_methods.py:100-110), against the run of the real
+    reference stored in the fixture."""
+    from maxent_b200 import engine
+    g = gc.load_golden("g8_marquardt_200x100.npz")
+    lm = engine.LMParams(marquardt=True, conv_rel_change=-1.0, conv_abs_change=float(g["lm_abs_change"]))
+    prob, res = gc.run_fixture(g, lm=lm)
+    assert prob.n_sv == int(g["ref_n_sv"])
+    gc.check_against_reference(g, res)
+    assert bool((res.status[0] & 1).all())
+    # the lock-step cross-check engine does not implement the variant and says so
+    prob1 = engine.SharedProblem(mo.tau_kernel(g["tau"], g["omega"], None), g["err"], mo.flat_default_model(g["omega"]),
+                                 mo.omega_delta(g["omega"]), reduce_singular_space=1e-11, engine=1)
+    with pytest.raises(Exception):
+        engine.run_sweep(prob1, g["G"], g["ref_alpha"], lm=lm)
+
+
 def test_known_answer_probability(torch_cuda):
     """The reference's literal numbers, test/python/tau_maxent.py:134-135 (6 decimals)."""
     g = gc.load_golden("g1_semicircular_prob.npz")

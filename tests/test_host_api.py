@@ -69,13 +69,16 @@ def test_convergence_trees_map_to_device_thresholds():
     assert (p.maxiter, p.miniter, p.mu0, p.nu, p.max_mu) == (1000, 0, 1e-18, 1.3, 1e20)
     assert (p.conv_max_derivative, p.conv_rel_change) == (1e-4, 1e-16)
     tree = mb.MaxDerivativeConvergenceMethod(1e-6) & mb.RelativeFunctionChangeConvergenceMethod(1e-12)
-    assert isinstance(tree, mb.AndConvergenceMethod) and tree.thresholds() == (1e-6, 1e-12)
-    assert mb.MaxDerivativeConvergenceMethod(1e-3).thresholds() == (1e-3, -1.0)
+    assert isinstance(tree, mb.AndConvergenceMethod) and tree.thresholds() == (1e-6, 1e-12, -1.0)
+    assert mb.MaxDerivativeConvergenceMethod(1e-3).thresholds() == (1e-3, -1.0, -1.0)
     assert (mb.NullConvergenceMethod() | mb.MaxDerivativeConvergenceMethod(1.0)).thresholds()[0] == np.inf
+    q = mb.LevenbergMinimizer(convergence=mb.FunctionChangeConvergenceMethod(1e-3) | mb.MaxDerivativeConvergenceMethod(1e-5),
+                              marquardt=True).lm_params()
+    assert (q.conv_max_derivative, q.conv_rel_change, q.conv_abs_change, q.marquardt) == (1e-5, -1.0, 1e-3, True)
+    assert q.c_struct().marquardt == 1 and q.c_struct().conv_abs_change == 1e-3
+    assert p.c_struct().marquardt == 0 and p.c_struct().conv_abs_change == -1.0
     with pytest.raises(NotImplementedError):
-        mb.LevenbergMinimizer(convergence=mb.FunctionChangeConvergenceMethod(1e-3)).lm_params()
-    with pytest.raises(NotImplementedError):
-        mb.LevenbergMinimizer(marquardt=True).lm_params()
+        mb.LevenbergMinimizer(J_squared=True).lm_params()
     with pytest.raises(Exception):
         mb.LevenbergMinimizer(nu=1.0).lm_params()          # levenberg_minimizer.py:139-140
     c = p.c_struct()

@@ -66,6 +66,16 @@ def test_bryan_bit_identical(golden_dir):
     _check_identical(out, g, fields=("chi2", "S", "Q", "A", "H"))
 
 
+def test_marquardt_and_function_change_bit_identical(golden_dir):
+    """LevenbergMinimizer(marquardt=True, convergence=MaxDerivative(1e-4) | FunctionChange(1e-9)) run by the real
+    reference (python/minimizers/levenberg_minimizer.py:181-185, convergence_methods.py:100-110)."""
+    g = _load(golden_dir, "g8_marquardt_200x100.npz")
+    out = _run(g, lm_options=dict(marquardt=bool(g["lm_marquardt"]), abs_change=float(g["lm_abs_change"])))
+    _check_identical(out, g, fields=("chi2", "S", "Q", "A", "H"))
+    base = _load(golden_dir, "g2_synth_200x100.npz")           # same data, default minimiser: a different path
+    assert not np.array_equal(g["ref_chi2"], base["ref_chi2"])
+
+
 @pytest.mark.parametrize("name", ["g5_config1_cut1e-11.npz", "g5b_config1_default_cut.npz"])
 def test_config1_bit_identical(golden_dir, name):
     """BASELINE config 1 (n_tau=1000, n_omega=400, 60 alphas): LineFit 23 / Chi2Curv 28 / Entropy 42."""
