@@ -46,14 +46,17 @@ def parse_args():
     ap.add_argument("--n-omega", type=int, default=1000)
     ap.add_argument("--n-alpha", type=int, default=60)
     ap.add_argument("--thr", type=float, default=1e-11, help="reduce_singular_space")
+    ap.add_argument("--cost-function", default="normal", choices=["normal", "plusminus", "bryan"],
+                    help="secondary measurements only: the headline metric is the default (normal) cost function")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-procs", type=int, default=0)
     return ap.parse_args()
 
 
 def workload_name(a):
-    return "bootstrap batch C5 shard: %d spectra/GPU, n_tau=%d, n_omega=%d, %d alphas, cut %g" % (
-        a.spectra, a.n_tau, a.n_omega, a.n_alpha, a.thr)
+    return "bootstrap batch C5 shard: %d spectra/GPU, n_tau=%d, n_omega=%d, %d alphas, cut %g%s" % (
+        a.spectra, a.n_tau, a.n_omega, a.n_alpha, a.thr,
+        "" if a.cost_function == "normal" else ", cost function " + a.cost_function)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -199,7 +202,7 @@ def run_native(a):
 
     # ---- the job: one BatchedTauMaxEnt per rank over its shard of the bootstrap batch ------------
     B = a.spectra
-    job = batched.BatchedTauMaxEnt(reduce_singular_space=a.thr, device=dev)
+    job = batched.BatchedTauMaxEnt(cost_function=a.cost_function, reduce_singular_space=a.thr, device=dev)
     t0 = time.time()
     G_host = batched.synthetic_bootstrap_batch(a.n_tau, a.n_omega, B, first=rank * B, seed=5, pin=True)
     job.set_kernel_tau(np.linspace(0.0, 40.0, a.n_tau), batched.hyperbolic_omega(-10.0, 10.0, a.n_omega), beta=40.0)
@@ -321,7 +324,7 @@ def run_native(a):
                          "frac_with_survey_formula": flops_survey / (kernel_ms * 1e-3) / 1e12 / peak,
                          "pipe": "FP64 (DMMA m8n8k4 + DFMA share one pipe on B200)", "peak_source": peak_src},
         }
-        if world == 1 and not a.no_cpu_baseline:
+        if world == 1 and not a.no_cpu_baseline and a.cost_function == "normal":
             try:
                 line["cpu_baseline"] = cpu_baseline_block(cpu_baseline(a))
             except Exception as e:        # the GPU numbers stay valid; say why the CPU leg is missing

@@ -77,6 +77,15 @@ class BatchedMaxEntResult(object):
     def A(self, b):
         return self.device.A[b].cpu().numpy()
 
+    def __len__(self):
+        return int(self.chi2.shape[0])
+
+    def __getitem__(self, b):
+        """``result[b]`` = ``result.spectrum(b)``."""
+        if not -len(self) <= b < len(self):
+            raise IndexError(b)
+        return self.spectrum(b % len(self))
+
     def analyzer(self, name):
         k = ANALYZER_NAMES.index(name)
         return dict(alpha_index=self.alpha_index[:, k], A_out=self.A_out[:, k])
@@ -112,7 +121,9 @@ class BatchedTauMaxEnt(object):
         self.G_threshold = G_threshold
         self.device = device
         self.svd = svd
-        self.minimizer = engine.LMParams() if minimizer is None else minimizer
+        # engine.LMParams, or a LevenbergMinimizer like the one MaxEntLoop takes (python/maxent_loop.py:83-94)
+        self.minimizer = (engine.LMParams() if minimizer is None else
+                          minimizer.lm_params() if hasattr(minimizer, "lm_params") else minimizer)
         self.omega = HyperbolicOmegaMesh(-10, 10, 100)
         self.alpha_mesh = LogAlphaMesh(1e-4, 20, 20)
         self.D = None

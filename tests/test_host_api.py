@@ -307,3 +307,13 @@ def test_file_setters(tmp_path):
     np.testing.assert_allclose(ew.maxent_diagonal.G, G)
     ew.set_G_tau_filename_pattern(str(tmp_path / "g_{i}_{j}.dat"), (3, 3))
     assert ew.shape == (3, 3)
+
+
+def test_batched_front_end_accepts_a_levenberg_minimizer():
+    """BatchedTauMaxEnt(minimizer=...) takes the same LevenbergMinimizer object MaxEntLoop does."""
+    import maxent_b200 as mb
+    from maxent_b200 import engine
+    job = mb.BatchedTauMaxEnt(minimizer=mb.LevenbergMinimizer(marquardt=True, maxiter=77))
+    assert isinstance(job.minimizer, engine.LMParams) and job.minimizer.marquardt and job.minimizer.maxiter == 77
+    assert isinstance(mb.BatchedTauMaxEnt().minimizer, engine.LMParams)
+    assert isinstance(mb.BatchedTauMaxEnt(minimizer=engine.LMParams(nu=1.5)).minimizer, engine.LMParams)
