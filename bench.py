@@ -195,8 +195,12 @@ def run_native(a):
         raise SystemExit("bench.py --impl native needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries the one JSON line: whatever the libraries print while the job runs (the NCCL version banner is
+    # written straight to file descriptor 1) goes to stderr; the descriptor is restored just before the line is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # NCCL writes its banner / debug lines to stdout by default; stdout carries the one JSON line
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
@@ -329,7 +333,10 @@ def run_native(a):
                 line["cpu_baseline"] = cpu_baseline_block(cpu_baseline(a))
             except Exception as e:        # the GPU numbers stay valid; say why the CPU leg is missing
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %s" % e}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 

@@ -289,15 +289,29 @@ def gather_results(out, dst=0):
                 t = t.cuda()
         sizes = [torch.zeros(1, dtype=torch.int64, device=t.device) for _ in range(world)]
         dist.all_gather(sizes, torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device))
+        # the ranks' shards land in slices of ONE buffer on dst (no concatenation pass); the host copy goes into
+        # pinned memory when the data is on a device (a pageable copy of the 2.6 GB of A_out of a 65,536-spectrum
+        # job ran at ~3 GB/s and dominated the gather)
+        counts = [int(n) for n in sizes]
         if rank == dst:
-            parts = [torch.empty((int(n),) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device) for n in sizes]
+            full = torch.empty((sum(counts),) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            parts = list(full.split(counts, 0)) if full.shape[0] else [full[:0] for _ in counts]
         else:
-            parts = None
-        if all(int(n) == int(sizes[0]) for n in sizes):
+            full = parts = None
+
+        def to_host(x):
+            if not x.is_cuda:
+                return x.numpy()
+            h = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
+            h.copy_(x, non_blocking=True)
+            torch.cuda.current_stream(x.device).synchronize()
+            return h.numpy()
+
+        if all(n == counts[0] for n in counts):
             # equal shards (the benchmark's case): one gather collective
             dist.gather(t, parts, dst=dst)
             if rank == dst:
-                got[name] = torch.cat(parts, 0).cpu().numpy()
+                got[name] = to_host(full)
             continue
         # ragged shards: point-to-point gather
         if rank == dst:
@@ -306,7 +320,7 @@ def gather_results(out, dst=0):
                     parts[r].copy_(t)
                 elif parts[r].numel():
                     dist.recv(parts[r], src=r)
-            got[name] = torch.cat(parts, 0).cpu().numpy()
+            got[name] = to_host(full)
         elif t.numel():
             dist.send(t, dst=dst)
     return got if rank == dst else None
