@@ -944,9 +944,15 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
             *reinterpret_cast<double2*>(sm + LY::o_J + t * 64 + 2 * lane) = make_double2(c[0], c[1]);
         }
         __syncthreads();
-        if (warp == 0) {                                       // smallest |J_kk| for the planner's equivalence pre-test
+        if (warp == 0) {
+            // floor for the planner's equivalence pre-test: two dampings can only give the same shifted diagonal
+            // if they differ by less than ~2 ulps of min_k |J_kk| / (d shift_k / d mu) + mu, where the shift of entry k
+            // is mu (Normal / PlusMinus), mu / Lambda_k (Bryan) or mu J_kk (Marquardt)
             double m = INFINITY;
-            for (int k = lane; k < s; k += 32) m = fmin(m, fabs(sm[LY::o_jd + k]));
+            for (int k = lane; k < s; k += 32) {
+                const double jd = fabs(sm[LY::o_jd + k]);
+                m = fmin(m, a.marquardt ? 1.0 : (bryan ? jd * sm[LY::o_lam + k] : jd));
+            }
             m = -warp_max(-m);
             if (lane == 0) ctl.jdmin = m;
         }
@@ -1215,7 +1221,7 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                     // with the smallest |J_kk| can only round to the same value if they differ by less than two of
                     // its ulps: cheap per-lane pre-test, the full comparison is rarely reached
                     auto maybe = [&](double ma, double mb) -> bool {
-                        return ma == mb || bryan || marq || !(fabs(ma - mb) > 4.5e-16 * (jdmin + fmax(ma, mb)));
+                        return ma == mb || !(fabs(ma - mb) > 4.5e-16 * (jdmin + fmax(ma, mb)));
                     };
                     auto equiv_full = [&](double ma, double mb) -> bool {
                         if (ma == mb) return true;
@@ -1328,7 +1334,7 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                         // everything on real values and re-plans when an entry is missing -- so a fast path can cost
                         // speculation efficiency but never change a result.
                         bool fast = false;
-                        if (!bryan && !marq) {
+                        {
                             const double nu = a.nu, inu = 1.0 / a.nu;
                             auto add_unique = [&](double mu) {
                                 if (lane == np) { p_mu = mu; p_slot = npu; }
