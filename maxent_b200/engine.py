@@ -320,7 +320,7 @@ def analyze(alpha, chi2, S, logp, A, gamma=0.2, linefit_deg=0, bryan_by_integrat
     and A_out[B, 5, n_omega] (None if A is None); with ``want_aux`` also aux[B, 4 + 2 n_alpha]
     (line-fit parameters, curvature, dS/dlog alpha)."""
     torch = _require_cuda()
-    lib = _lib.load()
+    _lib.load()                              # a missing library is an error here, not inside the operator
     dev = torch.device("cuda" if device is None else device)
     if torch.is_tensor(chi2) and chi2.is_cuda:
         dev = chi2.device
@@ -360,7 +360,6 @@ def run_sweep(prob, G, alpha_eff, probability=False, lm=None, chi2_factor=1.0, w
             raise ValueError("G has %d data points, kernel has %d" % (G.shape[1], prob.n_tau))
         alpha = _dev_f64(np.asarray(alpha_eff, dtype=np.float64) if not torch.is_tensor(alpha_eff) else alpha_eff, dev)
         n_alpha, s, n_omega = int(alpha.numel()), prob.n_sv, prob.n_omega
-        stream = _stream(dev)
         D_rows = v0_rows = None
         if D is not None:                    # one default model per spectrum, D[B, n_omega]
             D_rows, v0_rows = per_spectrum_models(prob, D, getattr(prob, "A_init_host", None))
