@@ -9,11 +9,11 @@ This file is a plain-numpy *restatement* of the algorithm TRIQS/maxent (v1.2.0) 
 
 Nothing under ``maxent_b200/`` may import it; the product path has no CPU fallback.
 
-Parity pin: ``oracle/validate_oracle.py`` runs the real reference (staged from
-``/root/reference`` by ``oracle/stage_reference.py``) next to this file and requires *bit-identical*
-chi2/S/Q/H/probability arrays and analyzer picks; ``tests/test_oracle_golden.py`` re-checks this
-file against the fixtures those runs produced (``tests/golden/*.npz``) and against the reference's
-own known-answer numbers (``test/python/tau_maxent.py:134-135``).
+Parity pin: ``oracle/make_golden.py`` runs the real reference (staged from ``/root/reference`` by
+``oracle/stage_reference.py``) and stores its inputs and outputs as ``tests/golden/*.npz``;
+``tests/test_oracle_golden.py`` requires this file to reproduce those chi2/S/Q/H/probability arrays and
+analyzer picks *bit for bit*, and checks the reference's own known-answer numbers
+(``test/python/tau_maxent.py:134-135``).
 
 The formulation is deliberately the reference's own (full kernel GEMVs, dense n_omega x n_omega
 Hessian, LU solves through ``np.linalg.solve``) -- NOT the singular-space formulation the CUDA

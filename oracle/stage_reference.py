@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Stage the (Python) TRIQS/maxent reference OUTSIDE the repository so it can be imported.
 
-TEST INFRASTRUCTURE ONLY.  Used by ``oracle/make_golden.py`` and ``oracle/validate_oracle.py``
+TEST INFRASTRUCTURE ONLY.  Used by ``oracle/make_golden.py``
 in the build container to (a) pin ``oracle/maxent_oracle.py`` against the real reference and
 (b) generate the fixtures under ``tests/golden/``.  The staged copy lives under ``/tmp`` (never in
 the repo, never on the GPU box): reference sources are not copied into this repository.
