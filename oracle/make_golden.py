@@ -174,6 +174,7 @@ def main():
     print("g6 done")
     preblur_case(m)
     marquardt_case(m)
+    mesh_case(m)
 
 
 def preblur_case(m):
@@ -201,8 +202,40 @@ def marquardt_case(m):
     print("g8", out["ref_n_sv"], out["ref_wall"], out.get("ref_idx_LineFitAnalyzer"), out["noise_A"])
 
 
+def mesh_case(m):
+    """G0: the host-side objects of tier T0 as the real reference builds them: the four omega meshes
+    with their integration weights (python/omega_meshes.py), the alpha meshes (python/alpha_meshes.py), the flat
+    default model (python/default_models.py:61-63) and a small TauKernel with K_delta (python/kernels.py:244-266)."""
+    out = {}
+    for name in ("LinearOmegaMesh", "LorentzianOmegaMesh", "LorentzianSmallerOmegaMesh", "HyperbolicOmegaMesh"):
+        for (lo, hi, n) in ((-10, 10, 10), (-7.5, 12.25, 57)):
+            mesh = getattr(m, name)(omega_min=lo, omega_max=hi, n_points=n)
+            key = "%s_%d" % (name, n)
+            out[key] = np.array(mesh)
+            out[key + "_delta"] = np.array(mesh.delta)
+            out[key + "_flatD"] = np.array(m.FlatDefaultModel(omega=mesh).D)
+    out["LogAlphaMesh"] = np.array(m.LogAlphaMesh(alpha_min=0.0001, alpha_max=20, n_points=20))
+    out["LogAlphaMesh_60"] = np.array(m.LogAlphaMesh(0.01, 2000, 60))
+    out["LinearAlphaMesh"] = np.array(m.LinearAlphaMesh(alpha_min=0.0001, alpha_max=20, n_points=20))
+    tau = np.linspace(0, 7.5, 23)
+    om = m.HyperbolicOmegaMesh(-6, 6, 31)
+    K = m.TauKernel(tau, om, 7.5)
+    out["kernel_tau"], out["kernel_omega"], out["kernel_K"], out["kernel_K_delta"] = tau, np.array(om), np.array(K.K), np.array(K.K_delta)
+    # DataDefaultModel on a different grid (python/default_models.py:83-113) and the preblur matrix (python/preblur.py:33-58)
+    om_in = np.linspace(-8, 8, 41)
+    dens = np.exp(-om_in**2 / 3.0) + 0.01
+    out["ddm_omega_in"], out["ddm_default"] = om_in, dens
+    out["ddm_D"] = np.array(m.DataDefaultModel(dens, om_in, om).D)
+    out["ddm_D_same_grid"] = np.array(m.DataDefaultModel(np.exp(-np.array(om)**2) + 0.1, om, om).D)
+    out["preblur_B"] = np.array(m.get_preblur(om, 0.4))
+    np.savez_compressed(os.path.join(GOLD, "g0_meshes.npz"), **out)
+    print("g0", len(out))
+
+
 if __name__ == "__main__":
-    if "--marquardt-only" in sys.argv:
+    if "--meshes-only" in sys.argv:
+        mesh_case(import_reference())
+    elif "--marquardt-only" in sys.argv:
         marquardt_case(import_reference())
     elif "--preblur-only" in sys.argv:
         preblur_case(import_reference())

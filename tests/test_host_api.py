@@ -317,3 +317,40 @@ def test_batched_front_end_accepts_a_levenberg_minimizer():
     assert isinstance(job.minimizer, engine.LMParams) and job.minimizer.marquardt and job.minimizer.maxiter == 77
     assert isinstance(mb.BatchedTauMaxEnt().minimizer, engine.LMParams)
     assert isinstance(mb.BatchedTauMaxEnt(minimizer=engine.LMParams(nu=1.5)).minimizer, engine.LMParams)
+
+
+def test_meshes_and_default_model_match_the_reference_exactly():
+    """Tier T0: omega meshes with their integration weights, alpha meshes and the flat default model
+    are the reference's arrays (tests/golden/g0_meshes.npz, written by oracle/make_golden.py from the real
+    python/omega_meshes.py, alpha_meshes.py, default_models.py); the oracle's TauKernel agrees to 1e-15
+    (test/python/tau_kernel.py:27-69).  Copies keep the mesh attributes (test/python/omega_meshes.py:62-73)."""
+    import copy
+    import os
+    import maxent_b200 as mb
+    from oracle import maxent_oracle as mo
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "g0_meshes.npz"))
+    for name in ("LinearOmegaMesh", "LorentzianOmegaMesh", "LorentzianSmallerOmegaMesh", "HyperbolicOmegaMesh"):
+        for (lo, hi, n) in ((-10, 10, 10), (-7.5, 12.25, 57)):
+            mesh = getattr(mb, name)(omega_min=lo, omega_max=hi, n_points=n)
+            key = "%s_%d" % (name, n)
+            np.testing.assert_array_equal(np.asarray(mesh), g[key], err_msg=key)
+            np.testing.assert_array_equal(np.asarray(mesh.delta), g[key + "_delta"], err_msg=key)
+            np.testing.assert_array_equal(mb.FlatDefaultModel(omega=mesh).D, g[key + "_flatD"], err_msg=key)
+            for c in (mesh.copy(), copy.deepcopy(mesh)):
+                assert np.all(c == mesh) and (c.omega_min, c.omega_max, c.n_points) == (lo, hi, n)
+    np.testing.assert_array_equal(np.asarray(mb.LogAlphaMesh(alpha_min=0.0001, alpha_max=20, n_points=20)), g["LogAlphaMesh"])
+    np.testing.assert_array_equal(np.asarray(mb.LogAlphaMesh(0.01, 2000, 60)), g["LogAlphaMesh_60"])
+    np.testing.assert_array_equal(np.asarray(mb.LinearAlphaMesh(alpha_min=0.0001, alpha_max=20, n_points=20)), g["LinearAlphaMesh"])
+    # oracle side of the same tier
+    np.testing.assert_array_equal(mo.hyperbolic_omega_mesh(-7.5, 12.25, 57), g["HyperbolicOmegaMesh_57"])
+    np.testing.assert_array_equal(mo.omega_delta(g["HyperbolicOmegaMesh_57"]), g["HyperbolicOmegaMesh_57_delta"])
+    np.testing.assert_array_equal(mo.log_alpha_mesh(0.01, 2000, 60), g["LogAlphaMesh_60"])
+    K = mo.tau_kernel(g["kernel_tau"], g["kernel_omega"], 7.5)
+    assert np.max(np.abs(K - g["kernel_K"])) < 1e-15
+    np.testing.assert_allclose(K * mo.omega_delta(g["kernel_omega"])[None, :], g["kernel_K_delta"], rtol=0, atol=1e-15)
+    # default model given on another grid, and the preblur matrix
+    om = mb.DataOmegaMesh(g["kernel_omega"])
+    np.testing.assert_allclose(mb.DataDefaultModel(g["ddm_default"], g["ddm_omega_in"], om).D, g["ddm_D"], rtol=1e-15, atol=0)
+    np.testing.assert_allclose(mb.DataDefaultModel(np.exp(-g["kernel_omega"]**2) + 0.1, om, om).D, g["ddm_D_same_grid"],
+                               rtol=1e-15, atol=0)
+    np.testing.assert_allclose(mb.get_preblur(om, 0.4), g["preblur_B"], rtol=1e-14, atol=1e-300)
