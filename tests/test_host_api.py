@@ -354,3 +354,36 @@ def test_meshes_and_default_model_match_the_reference_exactly():
     np.testing.assert_allclose(mb.DataDefaultModel(np.exp(-g["kernel_omega"]**2) + 0.1, om, om).D, g["ddm_D_same_grid"],
                                rtol=1e-15, atol=0)
     np.testing.assert_allclose(mb.get_preblur(om, 0.4), g["preblur_B"], rtol=1e-14, atol=1e-300)
+
+
+def test_caller_side_utilities(tmp_path, capsys):
+    """numder / check_der (python/maxent_util.py:170-237), the TRIQS switches of a USE_TRIQS=OFF build
+    (python/triqs_support.py.in:31-78) and the version report."""
+    import maxent_b200 as mb
+    x0 = np.array([[0.3, -1.2], [2.0, 0.5]])
+    f = lambda x: np.sum(np.sin(x) * x)
+    d = lambda x: (np.cos(x) * x + np.sin(x))[None]
+    J = mb.numder(f, x0)
+    assert J.shape == (1, 2, 2) and np.max(np.abs(J - d(x0))) < 1e-8
+    vec = lambda x: np.array([x[0] * x[1], x[0] ** 2, np.exp(x[1])])
+    Jv = mb.numder(vec, np.array([1.5, -0.5]))
+    assert Jv.shape == (3, 2)
+    np.testing.assert_allclose(Jv, [[-0.5, 1.5], [3.0, 0.0], [0.0, np.exp(-0.5)]], atol=1e-8)
+    assert mb.check_der(f, d, x0, name="ok")
+    assert not mb.check_der(f, lambda x: 1.01 * d(x), x0, name="wrong")
+    assert "wrong" in capsys.readouterr().out
+    assert mb.check_der(f, lambda x: (1 + 1e-10) * d(x), x0, renorm=True) and mb.check_der(f, d, x0, renorm=5.0)
+    assert mb.if_no_triqs() and not mb.if_triqs_1() and not mb.if_triqs_2()
+    with pytest.raises(NotImplementedError, match="only available with TRIQS"):
+        mb.get_G_tau_from_A_w(np.ones(3), np.linspace(-1, 1, 3), 10.0, 11)
+    with pytest.raises(NotImplementedError):
+        mb.get_G_w_from_A_w(np.ones(3), np.linspace(-1, 1, 3))
+    assert "TRIQS support" in mb.get_G_w_from_A_w.__doc__
+    a, b = tmp_path / "a.txt", tmp_path / "b.txt"
+    a.write_text("x  \ny\n\n"); b.write_text("x\ny\n")
+    mb.assert_text_files_equal(str(a), str(b))
+    b.write_text("x\nz\n")
+    with pytest.raises(AssertionError):
+        mb.assert_text_files_equal(str(a), str(b))
+    mb.show_version(); mb.show_git_hash()
+    assert "maxent_b200 version" in capsys.readouterr().out
