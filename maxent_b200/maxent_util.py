@@ -16,9 +16,12 @@ def numder(fun, x, delta=1.e-6):
     x = np.asarray(x)
     jac = None
     for idx in itertools.product(*[range(n) for n in x.shape]):
-        step = np.zeros(x.shape)
-        step[idx] = delta
-        up, down = np.asarray(fun(x + step)), np.asarray(fun(x - step))
+        # the lower point is reached from the upper one ((x_i + delta) - 2 delta), as in the reference: same rounding
+        hi = np.array(x, dtype=float)
+        hi[idx] += delta
+        lo = hi.copy()
+        lo[idx] -= 2 * delta
+        up, down = np.asarray(fun(hi)), np.asarray(fun(lo))
         if jac is None:
             lead = up.shape if up.ndim else (1,)
             jac = np.empty(lead + x.shape, dtype=up.dtype)
