@@ -32,5 +32,6 @@ from .batched import BatchedTauMaxEnt, BatchedMaxEntResult
 from .maxent_util import numder, check_der, get_G_w_from_A_w, get_G_tau_from_A_w
 from .triqs_support import if_no_triqs, if_triqs_1, if_triqs_2, require_triqs, assert_text_files_equal
 from .version import show_version, show_git_hash
+from .sigma_continuator import SigmaContinuator, DirectSigmaContinuator, InversionSigmaContinuator
 
 __version__ = "0.2"

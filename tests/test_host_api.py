@@ -379,6 +379,10 @@ def test_caller_side_utilities(tmp_path, capsys):
     with pytest.raises(NotImplementedError):
         mb.get_G_w_from_A_w(np.ones(3), np.linspace(-1, 1, 3))
     assert "TRIQS support" in mb.get_G_w_from_A_w.__doc__
+    for make in (lambda: mb.SigmaContinuator(), lambda: mb.DirectSigmaContinuator(None),
+                 lambda: mb.InversionSigmaContinuator(None, constant_shift=1.0)):
+        with pytest.raises(NotImplementedError, match="only available with TRIQS"):
+            make()
     a, b = tmp_path / "a.txt", tmp_path / "b.txt"
     a.write_text("x  \ny\n\n"); b.write_text("x\ny\n")
     mb.assert_text_files_equal(str(a), str(b))
