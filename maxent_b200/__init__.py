@@ -23,7 +23,7 @@ from .minimizers import (Minimizer, LevenbergMinimizer, ConvergenceMethod, AndCo
 from .probabilities import Probability, NormalLogProbability
 from .analyzers import (Analyzer, AnalyzerResult, LineFitAnalyzer, Chi2CurvatureAnalyzer, EntropyAnalyzer,
                         ClassicAnalyzer, BryanAnalyzer)
-from .maxent_result import MaxEntResult, MaxEntResultData
+from .maxent_result import MaxEntResult, MaxEntResultData, recursive_map, recursive_dtype, saved
 from .maxent_loop import MaxEntLoop
 from .preblur import get_preblur
 from .tau_maxent import TauMaxEnt

@@ -24,7 +24,9 @@ Kernel KernelSVD PreblurKernel TauKernel Logtaker VerbosityFlags MaxEntLoop MaxE
 LevenbergMinimizer ConvergenceMethod AndConvergenceMethod OrConvergenceMethod MaxDerivativeConvergenceMethod
 NullConvergenceMethod FunctionChangeConvergenceMethod RelativeFunctionChangeConvergenceMethod BaseOmegaMesh
 DataOmegaMesh HyperbolicOmegaMesh LinearOmegaMesh LorentzianOmegaMesh LorentzianSmallerOmegaMesh
-NormalLogProbability TauMaxEnt""".split()
+NormalLogProbability TauMaxEnt get_preblur check_der numder get_G_tau_from_A_w get_G_w_from_A_w SigmaContinuator
+DirectSigmaContinuator InversionSigmaContinuator if_no_triqs if_triqs_1 if_triqs_2 require_triqs
+assert_text_files_equal show_version show_git_hash""".split()
 
 
 def test_export_surface():
