@@ -175,6 +175,7 @@ def main():
     preblur_case(m)
     marquardt_case(m)
     mesh_case(m)
+    covariance_case(m)
 
 
 def preblur_case(m):
@@ -232,8 +233,52 @@ def mesh_case(m):
     print("g0", len(out))
 
 
+def covariance_case(m):
+    """G9: TauMaxEnt.set_cov with a full (correlated) covariance matrix (python/tau_maxent.py:253-288,
+    python/kernels.py:160-180) on the 200 x 100 problem: C_ij = sigma^2 (delta_ij + 0.4 exp(-|i-j| / 2.5))."""
+    n_tau, n_omega, sigma = 200, 100, 1.e-4
+    tau, _, om = synthetic(n_tau, n_omega)
+    K = m.TauKernel(tau, m.DataOmegaMesh(om), 40.0)
+    A = np.exp(-(om - 1.0)**2 / (2 * 0.5**2))
+    A /= np.trapz(A, om)
+    i = np.arange(n_tau)
+    C = sigma**2 * (np.eye(n_tau) + 0.4 * np.exp(-np.abs(i[:, None] - i[None, :]) / 2.5))
+    G = np.dot(K.K_delta, A) + np.dot(np.linalg.cholesky(C), np.random.RandomState(77).randn(n_tau))
+    amesh = np.array(m.LogAlphaMesh(0.05, 2000, 16))
+
+    def run(Gin):
+        tm = m.TauMaxEnt(reduce_singular_space=1e-11)
+        tm.set_verbosity(m.VerbosityFlags.Quiet)
+        tm.set_G_tau_data(np.array(tau), np.array(Gin))
+        tm.omega = m.DataOmegaMesh(np.array(om))
+        tm.alpha_mesh = m.DataAlphaMesh(amesh)
+        tm.set_cov(np.array(C))
+        return tm, tm.run()
+
+    tm, res = run(G)
+    _, res2 = run(G * (1.0 + 1.e-15))
+    A1, A2 = np.array(res.A), np.array(res2.A)
+    out = dict(tau=tau, G=G, cov=C, omega=np.array(om), alpha_mesh=amesh, variant="normal", use_probability=False,
+               reduce_singular_space=1e-11, err=np.array(tm.err), ref_alpha=np.array(res.alpha),
+               ref_chi2=np.array(res.chi2), ref_S=np.array(res.S), ref_Q=np.array(res.Q), ref_A=A1, ref_H=np.array(res.H),
+               ref_probability=np.array(res.probability, dtype=float), ref_n_sv=len(tm.K.S),
+               ref_G_rotated=np.array(tm.G), ref_K_rotated_row0=np.array(tm.K.K)[0],
+               noise_A=np.max(np.abs(A1 - A2), axis=1) / np.max(np.abs(A1), axis=1),
+               noise_chi2=np.abs(np.array(res2.chi2) / np.array(res.chi2) - 1.0),
+               noise_S=np.abs(np.array(res2.S) / np.array(res.S) - 1.0))
+    for name, ar in res.analyzer_results.items():
+        if hasattr(ar, "keys") and "alpha_index" in ar:
+            out["ref_idx_" + name] = int(ar["alpha_index"])
+            if ar.get("A_out", None) is not None:
+                out["ref_Aout_" + name] = np.array(ar["A_out"])
+    np.savez_compressed(os.path.join(GOLD, "g9_covariance_200x100.npz"), **out)
+    print("g9", out["ref_n_sv"], out.get("ref_idx_LineFitAnalyzer"), out["noise_A"])
+
+
 if __name__ == "__main__":
-    if "--meshes-only" in sys.argv:
+    if "--covariance-only" in sys.argv:
+        covariance_case(import_reference())
+    elif "--meshes-only" in sys.argv:
         mesh_case(import_reference())
     elif "--marquardt-only" in sys.argv:
         marquardt_case(import_reference())

@@ -88,6 +88,25 @@ def test_tau_maxent_marquardt_minimizer():
     assert np.all(res.converged)
 
 
+def test_full_covariance_matches_reference_run():
+    """TauMaxEnt.set_cov with a correlated covariance matrix (python/tau_maxent.py:253-288) against the run of the
+    real reference stored in tests/golden/g9_covariance_200x100.npz."""
+    g = gc.load_golden("g9_covariance_200x100.npz")
+    tm = mb.TauMaxEnt(reduce_singular_space=float(g["reduce_singular_space"]))
+    tm.set_verbosity(mb.VerbosityFlags.Quiet)
+    tm.set_G_tau_data(g["tau"], g["G"])
+    tm.omega = mb.DataOmegaMesh(g["omega"])
+    tm.alpha_mesh = mb.DataAlphaMesh(g["alpha_mesh"])
+    tm.set_cov(g["cov"])
+    np.testing.assert_allclose(tm.err, g["err"], rtol=1e-12)
+    np.testing.assert_allclose(tm.G, g["ref_G_rotated"], rtol=0, atol=1e-13)
+    res = tm.run()
+    assert len(tm.K.S) == int(g["ref_n_sv"])
+    np.testing.assert_allclose(res.alpha, g["ref_alpha"], rtol=1e-14)
+    gc.check_against_reference(g, _ResView(res), rtol_chi2_S=2e-7)
+    assert np.all(res.converged)
+
+
 def test_tau_maxent_vs_hand_assembled_loop():
     """test/python/tau_maxent.py:31-135: TauMaxEnt and a MaxEntLoop assembled from its parts give the same
     result field by field, and the probabilities are the reference's literal numbers to 6 decimals."""

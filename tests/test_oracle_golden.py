@@ -76,6 +76,24 @@ def test_marquardt_and_function_change_bit_identical(golden_dir):
     assert not np.array_equal(g["ref_chi2"], base["ref_chi2"])
 
 
+def test_full_covariance_bit_identical(golden_dir):
+    """TauMaxEnt.set_cov with a correlated covariance matrix run by the real reference (python/tau_maxent.py:253-288):
+    eigenbasis rotation T, K' = T K, G' = T G, err = sqrt(eigenvalues); the SVD stays that of the unrotated kernel
+    with U' = T U (python/kernels.py:160-180)."""
+    g = _load(golden_dir, "g9_covariance_200x100.npz")
+    K = mo.tau_kernel(g["tau"], g["omega"], None)
+    e, v = np.linalg.eigh(g["cov"])
+    keep = e >= 1.e-14                                     # cov_threshold default (python/tau_maxent.py:56)
+    e, T = e[keep], v[:, keep].conjugate().transpose()
+    np.testing.assert_array_equal(np.sqrt(e), g["err"])
+    np.testing.assert_array_equal(np.dot(T, g["G"]), g["ref_G_rotated"])
+    np.testing.assert_array_equal(np.dot(T, K)[0], g["ref_K_rotated_row0"])
+    U, S, V = mo.kernel_svd(K, float(g["reduce_singular_space"]))
+    out = mo.maxent_loop(np.dot(T, K), np.dot(T, g["G"]), np.sqrt(e), g["omega"], g["alpha_mesh"],
+                         reduce_singular_space=float(g["reduce_singular_space"]), svd=(np.dot(T, U), S, V))
+    _check_identical(out, g, fields=("chi2", "S", "Q", "A", "H"))
+
+
 @pytest.mark.parametrize("name", ["g5_config1_cut1e-11.npz", "g5b_config1_default_cut.npz"])
 def test_config1_bit_identical(golden_dir, name):
     """BASELINE config 1 (n_tau=1000, n_omega=400, 60 alphas): LineFit 23 / Chi2Curv 28 / Entropy 42."""
