@@ -29,7 +29,7 @@ extern "C" {
 
 /* sweep engines (MxProblem.engine) */
 #define MX_ENGINE_AUTO       0   /* = MX_ENGINE_SPECTRUM_CTA */
-#define MX_ENGINE_LOCKSTEP   1   /* several spectra per CTA marched in lock-step rounds (csrc/mx_sweep.cuh)   */
+#define MX_ENGINE_LOCKSTEP   1   /* retired (round-1 lock-step engine): requesting it returns MX_ERR_UNSUPPORTED */
 #define MX_ENGINE_SPECTRUM_CTA 2 /* one spectrum per CTA, speculative damping batches (csrc/mx_sweep2.cuh)    */
 
 /* cost-function variants (python/maxent_loop.py:106-121) */

@@ -7,7 +7,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmaxent_b200.so")
+# MAXENT_B200_LIB selects another build of the same library (A/B timing of kernel variants, tools/ab_bench.py)
+LIB_PATH = os.environ.get("MAXENT_B200_LIB") or os.path.join(HERE, "libmaxent_b200.so")
 
 MX_OK = 0
 MX_MAX_NSV = 80

@@ -310,7 +310,7 @@ int mx_sweep_config(int32_t n_sv, int32_t engine, int32_t* engine_used, int32_t*
     if (engine_used) *engine_used = eng;
     if (spectra_per_cta) *spectra_per_cta = t;
     if (smem_bytes) *smem_bytes = sm;
-    if (threads) *threads = eng == 2 ? 256 : NTHREADS;
+    if (threads) *threads = 256;
     return MX_OK;
 }
 
@@ -327,7 +327,6 @@ int64_t mx_sweep_workspace_bytes(const MxProblem* p, int32_t B) {
     int eng = 0, grid = 0;
     const int rc = dispatch_sweep(a, nullptr, true, p->engine, &eng, nullptr, nullptr, &grid);
     if (rc != MX_OK) return rc;
-    if (eng != 2) return WS_HEADER;
     if (grid <= 0) return MX_ERR_NO_DEVICE;
     return WS_HEADER + 8 * sweep_scratch_doubles(p->n_sv, p->n_omega, p->variant, grid);
 }

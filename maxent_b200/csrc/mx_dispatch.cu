@@ -1,12 +1,5 @@
-// Dispatch of the fused sweep over the compiled instantiations of the two engines.
+// Dispatch of the fused sweep over the compiled tile-count instantiations of the kernel.
 #include "mx_common.cuh"
-namespace mx {
-int sweep_nt4(const SweepArgs&, cudaStream_t, bool, int*, int*);
-int sweep_nt5(const SweepArgs&, cudaStream_t, bool, int*, int*);
-int sweep_nt6(const SweepArgs&, cudaStream_t, bool, int*, int*);
-int sweep_nt7(const SweepArgs&, cudaStream_t, bool, int*, int*);
-int sweep_nt8(const SweepArgs&, cudaStream_t, bool, int*, int*);
-}  // namespace mx
 namespace mx2 {
 int sweep2_nt4(const mx::SweepArgs&, cudaStream_t, bool, int*, int*);
 int sweep2_nt5(const mx::SweepArgs&, cudaStream_t, bool, int*, int*);
@@ -33,29 +26,18 @@ int dispatch_sweep(SweepArgs& a, cudaStream_t stream, bool query, int engine, in
     a.pk = pk;
     const int nt = (s + 7) / 8;
     if (nt > 10) return MX_ERR_UNSUPPORTED;
-    if (engine == 0) engine = 2;
-    if (engine == 1 && (nt > 8 || a.per_spec || a.marquardt || a.conv_absq >= 0.0)) return MX_ERR_UNSUPPORTED;
+    if (engine == 0) engine = MX_ENGINE_SPECTRUM_CTA;
+    if (engine != MX_ENGINE_SPECTRUM_CTA) return MX_ERR_UNSUPPORTED;       // the lock-step engine of round 1 is retired
     if (o_engine) *o_engine = engine;
-    if (engine == 2) {
-        if (o_t) *o_t = 1;
-        switch (nt) {
-            case 1: case 2: case 3: case 4: return mx2::sweep2_nt4(a, stream, query, o_smem, o_grid);
-            case 5: return mx2::sweep2_nt5(a, stream, query, o_smem, o_grid);
-            case 6: return mx2::sweep2_nt6(a, stream, query, o_smem, o_grid);
-            case 7: return mx2::sweep2_nt7(a, stream, query, o_smem, o_grid);
-            case 8: return mx2::sweep2_nt8(a, stream, query, o_smem, o_grid);
-            case 9: return mx2::sweep2_nt9(a, stream, query, o_smem, o_grid);
-            default: return mx2::sweep2_nt10(a, stream, query, o_smem, o_grid);
-        }
-    }
-    if (engine != 1) return MX_ERR_BAD_ARG;
-    if (o_grid) *o_grid = 0;
+    if (o_t) *o_t = 1;
     switch (nt) {
-        case 1: case 2: case 3: case 4: return sweep_nt4(a, stream, query, o_t, o_smem);
-        case 5: return sweep_nt5(a, stream, query, o_t, o_smem);
-        case 6: return sweep_nt6(a, stream, query, o_t, o_smem);
-        case 7: return sweep_nt7(a, stream, query, o_t, o_smem);
-        default: return sweep_nt8(a, stream, query, o_t, o_smem);
+        case 1: case 2: case 3: case 4: return mx2::sweep2_nt4(a, stream, query, o_smem, o_grid);
+        case 5: return mx2::sweep2_nt5(a, stream, query, o_smem, o_grid);
+        case 6: return mx2::sweep2_nt6(a, stream, query, o_smem, o_grid);
+        case 7: return mx2::sweep2_nt7(a, stream, query, o_smem, o_grid);
+        case 8: return mx2::sweep2_nt8(a, stream, query, o_smem, o_grid);
+        case 9: return mx2::sweep2_nt9(a, stream, query, o_smem, o_grid);
+        default: return mx2::sweep2_nt10(a, stream, query, o_smem, o_grid);
     }
 }
 }  // namespace mx

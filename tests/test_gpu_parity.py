@@ -58,11 +58,6 @@ def test_marquardt_damping_and_function_change_criterion(torch_cuda):
     assert prob.n_sv == int(g["ref_n_sv"])
     gc.check_against_reference(g, res)
     assert bool((res.status[0] & 1).all())
-    # the lock-step cross-check engine does not implement the variant and says so
-    prob1 = engine.SharedProblem(mo.tau_kernel(g["tau"], g["omega"], None), g["err"], mo.flat_default_model(g["omega"]),
-                                 mo.omega_delta(g["omega"]), reduce_singular_space=1e-11, engine=1)
-    with pytest.raises(Exception):
-        engine.run_sweep(prob1, g["G"], g["ref_alpha"], lm=lm)
 
 
 def test_known_answer_probability(torch_cuda):
@@ -159,12 +154,8 @@ def test_maxiter_flags_not_converged(torch_cuda):
     np.testing.assert_array_equal((res.status[0].cpu().numpy() & 1).astype(bool), o["converged"])
     assert not o["converged"].all()
     # An unconverged iterate depends on the (arbitrary) singular vectors next to the cut, i.e. on the SVD
-    # implementation: exact agreement is only required between the two engines, which share the basis.
+    # implementation, so only a loose agreement with the oracle is required here.
     np.testing.assert_allclose(res.chi2[0].cpu().numpy(), o["chi2"], rtol=1e-4)
-    prob1 = engine.SharedProblem(K, g["err"], D, mo.omega_delta(g["omega"]), reduce_singular_space=1e-11, engine=1)
-    res1 = engine.run_sweep(prob1, g["G"], g["ref_alpha"], lm=engine.LMParams(maxiter=3))
-    np.testing.assert_allclose(res.chi2[0].cpu().numpy(), res1.chi2[0].cpu().numpy(), rtol=1e-11)
-    np.testing.assert_array_equal(res.n_solve[0].cpu().numpy(), res1.n_solve[0].cpu().numpy())
 
 
 def test_huge_alpha_returns_default_model(torch_cuda):
