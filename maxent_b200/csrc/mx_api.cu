@@ -310,7 +310,7 @@ int mx_sweep_config(int32_t n_sv, int32_t engine, int32_t* engine_used, int32_t*
     if (engine_used) *engine_used = eng;
     if (spectra_per_cta) *spectra_per_cta = t;
     if (smem_bytes) *smem_bytes = sm;
-    if (threads) *threads = 256;
+    if (threads) *threads = sweep_threads();
     return MX_OK;
 }
 

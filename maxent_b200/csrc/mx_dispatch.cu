@@ -8,9 +8,12 @@ int sweep2_nt7(const mx::SweepArgs&, cudaStream_t, bool, int*, int*);
 int sweep2_nt8(const mx::SweepArgs&, cudaStream_t, bool, int*, int*);
 int sweep2_nt9(const mx::SweepArgs&, cudaStream_t, bool, int*, int*);
 int sweep2_nt10(const mx::SweepArgs&, cudaStream_t, bool, int*, int*);
+int sweep2_threads();
 }  // namespace mx2
 
 namespace mx {
+
+int sweep_threads() { return mx2::sweep2_threads(); }
 
 int64_t sweep_scratch_doubles(int n_sv, int n_omega, int variant, int grid) {
     (void)n_sv;

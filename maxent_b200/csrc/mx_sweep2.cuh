@@ -1,13 +1,15 @@
-// Fused MaxEnt alpha sweep for sm_100a (B200), second generation ("spectrum per CTA").
+// Fused MaxEnt alpha sweep for sm_100a (B200), "spectrum per CTA".
 //
-// One 8-warp CTA owns one spectrum at a time (persistent CTAs, atomic work counter, 2 CTAs per SM at 128
-// registers per thread; the four solver warps borrow the other warp group's registers with setmaxnreg
-// while they hold a whole matrix in registers) and runs the whole alpha mesh for it.  The Levenberg-Marquardt iteration of the reference
+// One CTA of MX_NWARP warps (8; 4 is supported) owns one spectrum at a time (persistent CTAs, atomic work counter, as
+// many CTAs per SM as registers and shared memory allow: two at 8 warps) and runs the whole alpha mesh for it.
+// Round 2 measured the alternatives on B200 (profiles/r02_ab_*.log): four 4-warp CTAs per SM are 10 % slower, three
+// 4-warp CTAs at 168 registers 3 % slower than two 8-warp CTAs -- the FP64 pipe is 62-68 % busy in all three, so the
+// idle third is not a matter of how the warps are grouped.  The Levenberg-Marquardt iteration of the reference
 // (levenberg_minimizer.py:123-248) asks for Q(v - dv(mu)) at a chain of damping values
 // mu, 1.3 mu, 1.3^2 mu ... that is decided by comparisons of the Q values.  Instead of evaluating the
 // chain one trial at a time (latency bound), the CTA *speculates*: it plans the next up-to-8 damping
-// values the reference would visit, factorises the 8 shifted Hessians (one warp per matrix, four at a
-// time, register-resident DMMA-blocked Cholesky) and evaluates the 8 trial vectors in ONE pass over
+// values the reference would visit, factorises the 8 shifted Hessians (one warp per matrix, DMMA-blocked "lean"
+// Cholesky) and evaluates the 8 trial vectors in ONE pass over
 // V' where the 8 trials are the M dimension of the FP64 tensor-core MMA (m8n8k4):
 //     T-pass:  x = V' t_b ; H = D exp(x) ; y_b = V'^T H ; S_b ; w_b -> scratch      (8 trials)
 //     H-pass:  Z = V'^T diag(w) V'                                                   (accepted point)
@@ -23,8 +25,9 @@
 // gives the Cholesky trailing updates, J = eta Z Lambda Z + alpha Z and f = Z u without any layout
 // conversion.  tools/lane_model.py is the numpy model these routines were derived from.
 //
-// V' streams L2 -> shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier, 4 stages) in the
-// swizzled 8x8-tile layout written by mx_layout_V.
+// V' streams L2 -> shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier) in the
+// swizzled 8x8-tile layout written by mx_layout_V.  A bulk copy costs the CTA ~360 cycles whatever its size
+// (tools/tma_stream_bench.cu), so a chunk is one copy of NWARP k-tiles: one tile per warp and step in the T-pass.
 #pragma once
 #include <stdlib.h>
 #include "mx_common.cuh"
@@ -35,18 +38,17 @@ using mx::SweepArgs;
 using mx::dmma;
 using mx::tile_off;
 
-constexpr int NWARP = 8;        // two warp groups: group 0 also runs the register-hungry Cholesky phase
-constexpr int NSOLVE = 4;       // warps that factorise (one warp group, see regs_to_solvers)
+#ifndef MX_NWARP
+#define MX_NWARP 8
+#endif
+#ifndef MX_CTAS_PER_SM          // CTAs per SM the kernel is compiled for: register cap = 64K / (CTAs x threads)
+#define MX_CTAS_PER_SM (MX_NWARP == 4 ? 4 : 2)
+#endif
+constexpr int NWARP = MX_NWARP;
+static_assert(NWARP == 4 || NWARP == 8, "the reduction trees are written for 4 or 8 warps");
 constexpr int NTHR = NWARP * 32;
-constexpr int REG_HI = 216, REG_LO = 40, REG_EVEN = 128;   // setmaxnreg budgets: 128 * (216 + 40) = 256 * 128
-constexpr int CH = 4;          // k-tiles (8 omega rows each) per staged chunk = one per warp in the T-pass
-// Number of staging buffers of the V' stream.  The cost pass consumes two chunks per step, NST - 2 are in flight
-// while it computes.  Five and six stages (more bytes in flight) were measured on B200 and bought nothing: with one
-// CTA per SM the pass takes 18 us per batch against a DMMA-pipe bound of 9 us either way.  A diagnostic build that
-// skipped parts of the pass showed why: 7.5 us of it is the exp() of the 8 x n_omega trial points -- a dependent FP64
-// chain with only two evaluations in flight per thread and two to four warps per scheduler -- not the L2 -> SM stream
-// (an Estrin-scheme exp with half the chain depth was slower: it spills at the 128-register cap).
-__host__ __device__ constexpr int stage_count(int) { return 4; }
+constexpr int NKG = NWARP / 2;  // k-groups of the H-pass (two warps -- the two halves of the triangle -- per group)
+constexpr int CH = NWARP;       // k-tiles (8 omega rows each) per staged chunk = one per warp in the T-pass, two per k-group in the H-pass
 constexpr int MAXB = 8;        // unique trials per batch = M of the MMA
 constexpr int NTAB = 32;       // damping values tabulated per batch (several may share one unique trial)
 constexpr int NROWS = 9;       // scratch rows per CTA: 8 trials + 1 carried candidate
@@ -135,6 +137,48 @@ __device__ __forceinline__ void mma_nt(double (&c)[2], double x0, double x1, dou
 __host__ __device__ constexpr int tri(int I, int J) { return I * (I + 1) / 2 + J; }
 
 // ------------------------------------------------------------------------------------------
+// sizes of the "lean" blocked Cholesky (see below): how many tiles of the factor a warp parks in shared memory
+// ------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int lean_nsm(int NT) {
+    int nsm = 0;
+    while (nsm < NT && (NT - 1 - nsm) * (NT - nsm) / 2 > 10) ++nsm;
+    return nsm;
+}
+__host__ __device__ constexpr int lean_nsmt(int NT) {          // strictly-lower tiles of the factor a warp parks in shared memory
+    const int nsm = lean_nsm(NT);
+    return NT * (NT - 1) / 2 - (NT - 1 - nsm) * (NT - nsm) / 2;
+}
+template <int NT>
+struct Lean {
+    static constexpr int NSM = lean_nsm(NT);                                   // block columns kept in shared memory
+    static constexpr int NREG = (NT - 1 - NSM) * (NT - NSM) / 2;               // strictly-lower tiles kept in registers
+    static constexpr int NSMT = NT * (NT - 1) / 2 - NREG;                      // tiles per warp in shared memory
+    static constexpr int RDIM = NREG > 0 ? NREG : 1;
+    __host__ __device__ static constexpr int before(int J, int from) {
+        int o = 0;
+        for (int j = from; j < J; ++j) o += NT - 1 - j;
+        return o;
+    }
+    __host__ __device__ static constexpr int sidx(int I, int J) { return before(J, 0) + I - J - 1; }
+    __host__ __device__ static constexpr int ridx(int I, int J) { return J >= NSM ? before(J, NSM) + I - J - 1 : 0; }
+};
+
+// Staging buffers of the V' stream: at least two (one being consumed, one in flight), and enough area for what the
+// ring is reused for between passes: Zfull (NT x NT tiles), the parked Cholesky tiles of every warp, the per-warp y
+// partials of the T-pass.  MX_NST_EXTRA adds stages (deeper prefetch) when the CTAs-per-SM target leaves room.
+#ifndef MX_NST_EXTRA
+#define MX_NST_EXTRA 0
+#endif
+__host__ __device__ constexpr int stage_count(int NT) {
+    int need = NT * NT;                                                          // in 8x8 tiles
+    if (NWARP * lean_nsmt(NT) > need) need = NWARP * lean_nsmt(NT);
+    if (NWARP * NT > need) need = NWARP * NT;
+    int nst = (need + CH * NT - 1) / (CH * NT);
+    if (nst < 2) nst = 2;
+    return nst + MX_NST_EXTRA;
+}
+
+// ------------------------------------------------------------------------------------------
 // shared-memory layout (offsets in doubles)
 // ------------------------------------------------------------------------------------------
 template <int NT>
@@ -143,13 +187,12 @@ struct Lay {
     static constexpr int NTRI = NT * (NT + 1) / 2;
     static constexpr int STAGE_D = CH * NT * 64;
     static constexpr int NST = stage_count(NT);
-    static constexpr int o_stage = 0;                              // NST x STAGE_D ; aliases: Zfull [NT*NT*64], yred [NWARP][8][SP]
-    static constexpr int o_J = o_stage + NST * STAGE_D;         // NTRI tiles, C layout
-    static constexpr int o_tb = o_J + NTRI * 64;                   // [8][SP] trial vectors t_b = v - dv_b
-    static constexpr int o_dvb = o_tb + MAXB * SP;                 // [8][SP]
-    static constexpr int o_yb = o_dvb + MAXB * SP;                 // [8][SP]
-    static constexpr int o_cdv = o_yb + MAXB * SP;                 // carried candidate: dv, y
-    static constexpr int o_cy = o_cdv + SP;
+    static constexpr int o_stage = 0;                              // NST x STAGE_D ; aliases: Zfull [NT*NT*64], yred [NWARP][8][SP], parked Cholesky tiles
+    static constexpr int o_J = o_stage + NST * STAGE_D;         // NTRI tiles, C layout (also: partial Z tiles of the H-pass, parked tiles of the log-det)
+    static constexpr int o_tb = o_J + NTRI * 64;                   // [8][SP] trial vectors t_b = v - dv_b  (the accepted one IS the new v, levenberg_minimizer.py:239)
+    static constexpr int o_yb = o_tb + MAXB * SP;                  // [8][SP]
+    static constexpr int o_ctb = o_yb + MAXB * SP;                 // carried candidate: t, y
+    static constexpr int o_cy = o_ctb + SP;
     static constexpr int o_v = o_cy + SP;
     static constexpr int o_f = o_v + SP;
     static constexpr int o_rhs = o_f + SP;
@@ -165,6 +208,9 @@ struct Lay {
     static constexpr int total = o_bar + 2 * NST;
     static_assert(NT * NT * 64 <= NST * STAGE_D, "Zfull must fit in the staging area");
     static_assert(NWARP * 8 * SP <= NST * STAGE_D, "yred must fit in the staging area");
+    static_assert(NWARP * Lean<NT>::NSMT * 64 <= NST * STAGE_D, "the parked Cholesky tiles must fit in the staging area");
+    static_assert(Lean<NT>::NSMT <= NTRI, "the parked tiles of the log-det factorisation must fit in the J area");
+    static_assert(NT * NT * 64 + (NKG - 1) * NTRI * 64 <= o_ctb, "partial Z tiles of the H-pass must fit behind Zfull");
 };
 
 enum { PH_FIRST = 0, PH_PUMP, PH_PROBE, PH_WALK, PH_DONE };
@@ -192,6 +238,9 @@ struct Ctl {
     unsigned gchunk;           // chunks streamed so far (pipeline phase bookkeeping)
     long long t_last;          // phase timers (clock64 of thread 0), see MX_PHASE_*
     long long tph[8];
+#ifdef MX_TPROF
+    long long pf[16];
+#endif
 };
 enum { PHT_PLAN = 0, PHT_SOLVE, PHT_TPASS, PHT_HPASS, PHT_GRAD, PHT_FORMJ, PHT_OTHER, PHT_REPLAY };
 static_assert(sizeof(Ctl) <= 192 * sizeof(double), "Ctl must fit its reserved block");
@@ -246,138 +295,13 @@ __device__ bool lm_run(LM& s, double nu, double max_mu, double eps_nu, Look&& lo
 }
 
 // ------------------------------------------------------------------------------------------
-// register-resident blocked Cholesky of an (8 NT)^2 SPD matrix held as lower 8x8 tiles in C layout
+// "lean" blocked L D L^T factorisation of a shifted Hessian by ONE warp: left-looking, at most 10 strictly-lower tiles
+// stay in registers, the leading block columns are parked in a per-warp slice of shared memory, the diagonal tiles are
+// dropped once the inverse U = L_d^{-T} of their unit factor is known.  ~100 registers per thread, so every warp of the
+// CTA factorises its own matrix at the same time.  The stored tiles are Y = L D (unscaled columns) and the reciprocal
+// pivots 1/d; a Cholesky factor would need 1/sqrt(d) per pivot as well -- a fifth of the solver's instructions on B200
+// (profiles/r02a_sweep2_stalls_by_line.txt) for no numerical benefit.  A non-positive pivot = not positive definite.
 // ------------------------------------------------------------------------------------------
-// Panel step for block column JB: right-looking Cholesky of the diagonal tile together with an identity tile E
-// (which becomes U = L_d^{-T}); the tiles below are then solved with two MMAs each: L[I][JB] = A[I][JB] U =
-// A[I][JB] W^T with W = U^T = L_d^{-1} (in-register transpose of U).
-template <int NT, int JB>
-__device__ __forceinline__ void chol_panel(double (&A)[Lay<NT>::NTRI][2], double (&U)[NT][2], bool& ok, double& logdet,
-                                           bool want_logdet, int r, int q, int lane) {
-    double E[2];
-    E[0] = (r == 2 * q) ? 1.0 : 0.0;
-    E[1] = (r == 2 * q + 1) ? 1.0 : 0.0;
-    double(&P0)[2] = A[tri(JB, JB)];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int jq = j >> 1, je = j & 1;
-        // The trailing update uses the UNSCALED column j and 1/a_jj, so the next pivot depends only on the short
-        // reciprocal chain; 1/sqrt(a_jj), which only the final values of column j need, runs beside it.
-        const double ajj = shfl(P0[je], 4 * j + jq);
-        const double lk0 = shfl(P0[je], 8 * q + jq);              // a[2q][j]
-        const double lk1 = shfl(P0[je], 8 * q + 4 + jq);          // a[2q+1][j]
-        const int src = (lane & ~3) | jq;
-        const double lp = shfl(P0[je], src);                      // a[r][j]
-        const double le = shfl(E[je], src);
-        if (!(ajj > 0.0)) ok = false;
-        if (want_logdet) logdet += log(ajj);
-        const double inv = rcp_nr(ajj);
-        const double rinv = rsqrt_nr(ajj);
-        const double p0 = lp * lk0, p1 = lp * lk1, e0 = le * lk0, e1 = le * lk1;
-        if (2 * q > j) { P0[0] = fma(-p0, inv, P0[0]); E[0] = fma(-e0, inv, E[0]); }
-        if (2 * q + 1 > j) { P0[1] = fma(-p1, inv, P0[1]); E[1] = fma(-e1, inv, E[1]); }
-        if (q == jq) { P0[je] *= rinv; E[je] *= rinv; }          // final values of column j
-    }
-    if (r < 2 * q) P0[0] = 0.0;
-    if (r < 2 * q + 1) P0[1] = 0.0;
-    U[JB][0] = E[0];
-    U[JB][1] = E[1];
-    if constexpr (JB + 1 < NT) {
-        // W[r][2q+e] = U[2q+e][r], which lives in lane (2q+e, r/2), register r%2
-        const int s0 = 8 * q + (r >> 1), s1 = s0 + 4;
-        const double a0 = shfl(E[0], s0), b0 = shfl(E[1], s0);
-        const double a1 = shfl(E[0], s1), b1 = shfl(E[1], s1);
-        const double W0 = (r & 1) ? b0 : a0, W1 = (r & 1) ? b1 : a1;
-#pragma unroll
-        for (int I = JB + 1; I < NT; ++I) {
-            double c[2] = {0.0, 0.0};
-            mma_nt(c, A[tri(I, JB)][0], A[tri(I, JB)][1], W0, W1);
-            A[tri(I, JB)][0] = c[0];
-            A[tri(I, JB)][1] = c[1];
-        }
-    }
-}
-
-template <int NT, int JB>
-__device__ __forceinline__ void chol_steps(double (&A)[Lay<NT>::NTRI][2], double (&U)[NT][2], bool& ok, double& logdet,
-                                           bool want_logdet, int r, int q, int lane) {
-    if constexpr (JB < NT) {
-        chol_panel<NT, JB>(A, U, ok, logdet, want_logdet, r, q, lane);
-        // trailing update A[I][J] -= L[I][JB] L[J][JB]^T
-#pragma unroll
-        for (int I = JB + 1; I < NT; ++I) {
-            const double n0 = -A[tri(I, JB)][0], n1 = -A[tri(I, JB)][1];
-#pragma unroll
-            for (int J = JB + 1; J <= I; ++J) mma_nt(A[tri(I, J)], n0, n1, A[tri(J, JB)][0], A[tri(J, JB)][1]);
-        }
-        chol_steps<NT, JB + 1>(A, U, ok, logdet, want_logdet, r, q, lane);
-    }
-}
-
-// Solve L L^T x = rhs with the factor in registers.  rhs: shared vector (8 NT); x is returned
-// row-replicated: xr[I] = x[8 I + r] on every lane of row r.  The intermediate z = L^{-1} rhs is parked in
-// `zscr` (8 NT doubles of shared memory owned by this warp) to keep the register footprint down.
-template <int NT>
-__device__ __forceinline__ void chol_solve(const double (&A)[Lay<NT>::NTRI][2], const double (&U)[NT][2],
-                                           const double* __restrict__ rhs, double (&xr)[NT], int r, int q,
-                                           double* __restrict__ zscr) {
-    {
-        double zc[NT][2];
-#pragma unroll
-        for (int jb = 0; jb < NT; ++jb) {
-            double acc = 0.0;
-#pragma unroll
-            for (int J = 0; J < jb; ++J) acc = fma(A[tri(jb, J)][0], zc[J][0], fma(A[tri(jb, J)][1], zc[J][1], acc));
-            double rr = rhs[8 * jb + r];
-            if (jb > 0) rr -= quadreduce(acc);
-            zc[jb][0] = colreduce(U[jb][0] * rr);
-            zc[jb][1] = colreduce(U[jb][1] * rr);
-            if (r == 0) *reinterpret_cast<double2*>(zscr + 8 * jb + 2 * q) = make_double2(zc[jb][0], zc[jb][1]);
-        }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int jb = NT - 1; jb >= 0; --jb) {
-        double c0 = 0.0, c1 = 0.0;
-#pragma unroll
-        for (int I = jb + 1; I < NT; ++I) {
-            c0 = fma(A[tri(I, jb)][0], xr[I], c0);
-            c1 = fma(A[tri(I, jb)][1], xr[I], c1);
-        }
-        const double2 z = *reinterpret_cast<const double2*>(zscr + 8 * jb + 2 * q);
-        double z0 = z.x, z1 = z.y;
-        if (jb < NT - 1) { z0 -= colreduce(c0); z1 -= colreduce(c1); }
-        xr[jb] = quadreduce(fma(U[jb][0], z0, U[jb][1] * z1));
-    }
-    __syncwarp();
-}
-
-// ------------------------------------------------------------------------------------------
-// "lean" blocked Cholesky (NT <= 7): left-looking, at most 10 strictly-lower tiles of L stay in registers, the
-// leading block columns are parked in a per-warp slice of shared memory, the diagonal tiles are dropped once
-// their inverse U is known.  ~100 registers per thread instead of ~210, so ALL eight warps of the CTA can
-// factorise at the same time (eight damping trials per round) without borrowing registers via setmaxnreg.
-// ------------------------------------------------------------------------------------------
-__host__ __device__ constexpr int lean_nsm(int NT) {
-    int nsm = 0;
-    while (nsm < NT && (NT - 1 - nsm) * (NT - nsm) / 2 > 10) ++nsm;
-    return nsm;
-}
-template <int NT>
-struct Lean {
-    static constexpr int NSM = lean_nsm(NT);                                   // block columns kept in shared memory
-    static constexpr int NREG = (NT - 1 - NSM) * (NT - NSM) / 2;               // strictly-lower tiles kept in registers
-    static constexpr int NSMT = NT * (NT - 1) / 2 - NREG;                      // tiles per warp in shared memory
-    static constexpr int RDIM = NREG > 0 ? NREG : 1;
-    __host__ __device__ static constexpr int before(int J, int from) {
-        int o = 0;
-        for (int j = from; j < J; ++j) o += NT - 1 - j;
-        return o;
-    }
-    __host__ __device__ static constexpr int sidx(int I, int J) { return before(J, 0) + I - J - 1; }
-    __host__ __device__ static constexpr int ridx(int I, int J) { return J >= NSM ? before(J, NSM) + I - J - 1 : 0; }
-};
-
 // strictly-lower tile (I, J) of the factor: shared memory for the leading columns, registers for the rest
 template <int NT>
 __device__ __forceinline__ double2 lean_tile(const double* __restrict__ Lsm, const double (&R)[Lean<NT>::RDIM][2], int I, int J,
@@ -388,9 +312,14 @@ __device__ __forceinline__ double2 lean_tile(const double* __restrict__ Lsm, con
 
 // block column JB: C[I] = in(I, JB) - sum_{K<JB} L[I][K] L[JB][K]^T, Cholesky of the diagonal tile together with an
 // identity tile (-> U = L_d^{-T}), L[I][JB] = C[I] U for the tiles below (same arithmetic as chol_panel above)
-template <int NT, int JB, class Load>
+// With FWD the forward substitution z = L^{-1} rhs rides along: block jb of z is formed as soon as block column jb of
+// the factor is final, so its dependent chain (dot products, two shuffle reductions) overlaps the pivot chain of the
+// next block column instead of following the factorisation (same arithmetic as a separate forward sweep).
+template <int NT, int JB, bool FWD, class Load>
 __device__ __forceinline__ void lean_steps(Load& load, double* __restrict__ Lsm, double (&R)[Lean<NT>::RDIM][2], double (&U)[NT][2],
-                                           bool& ok, double& logdet, bool want_logdet, int r, int q, int lane) {
+                                           bool& ok, double& logdet, bool want_logdet, int r, int q, int lane,
+                                           const double* __restrict__ rhs, double (&zc)[NT][2], double* __restrict__ zscr,
+                                           double* __restrict__ dinv) {
     if constexpr (JB < NT) {
         constexpr int NC = NT - JB;
         double C[NC][2];
@@ -398,12 +327,15 @@ __device__ __forceinline__ void lean_steps(Load& load, double* __restrict__ Lsm,
         for (int i = 0; i < NC; ++i) { const double2 t = load(JB + i, JB); C[i][0] = t.x; C[i][1] = t.y; }
 #pragma unroll
         for (int K = 0; K < JB; ++K) {
+            // stored tiles are Y = L D (unscaled columns); the update is Y_i D^-1 Y_JB^T
             const double2 y = lean_tile<NT>(Lsm, R, JB, K, lane);
-            mma_nt(C[0], -y.x, -y.y, y.x, y.y);
+            const double2 dk = *reinterpret_cast<const double2*>(dinv + 8 * K + 2 * q);
+            const double ys0 = y.x * dk.x, ys1 = y.y * dk.y;
+            mma_nt(C[0], -y.x, -y.y, ys0, ys1);
 #pragma unroll
             for (int i = 1; i < NC; ++i) {
                 const double2 x = lean_tile<NT>(Lsm, R, JB + i, K, lane);
-                mma_nt(C[i], -x.x, -x.y, y.x, y.y);
+                mma_nt(C[i], -x.x, -x.y, ys0, ys1);
             }
         }
         double E[2];
@@ -422,12 +354,12 @@ __device__ __forceinline__ void lean_steps(Load& load, double* __restrict__ Lsm,
             if (!(ajj > 0.0)) ok = false;
             if (want_logdet) logdet += log(ajj);
             const double inv = rcp_nr(ajj);
-            const double rinv = rsqrt_nr(ajj);
             const double p0 = lp * lk0, p1 = lp * lk1, e0 = le * lk0, e1 = le * lk1;
             if (2 * q > j) { P0[0] = fma(-p0, inv, P0[0]); E[0] = fma(-e0, inv, E[0]); }
             if (2 * q + 1 > j) { P0[1] = fma(-p1, inv, P0[1]); E[1] = fma(-e1, inv, E[1]); }
-            if (q == jq) { P0[je] *= rinv; E[je] *= rinv; }          // final values of column j
+            if (lane == 0) dinv[8 * JB + j] = inv;                   // 1 / d_j, kept in this warp's row of shared memory
         }
+        __syncwarp();
         U[JB][0] = E[0];
         U[JB][1] = E[1];
         if constexpr (NC > 1) {
@@ -448,32 +380,31 @@ __device__ __forceinline__ void lean_steps(Load& load, double* __restrict__ Lsm,
                 }
             }
         }
-        lean_steps<NT, JB + 1>(load, Lsm, R, U, ok, logdet, want_logdet, r, q, lane);
+        if constexpr (FWD) {
+            double acc = 0.0;
+#pragma unroll
+            for (int J = 0; J < JB; ++J) {
+                const double2 t = lean_tile<NT>(Lsm, R, JB, J, lane);
+                acc = fma(t.x, zc[J][0], fma(t.y, zc[J][1], acc));
+            }
+            double rr = rhs[8 * JB + r];
+            if (JB > 0) rr -= quadreduce(acc);
+            const double z0 = colreduce(U[JB][0] * rr), z1 = colreduce(U[JB][1] * rr);       // z = L^-1 rhs (unit L)
+            if (r == 0) *reinterpret_cast<double2*>(zscr + 8 * JB + 2 * q) = make_double2(z0, z1);
+            const double2 dj = *reinterpret_cast<const double2*>(dinv + 8 * JB + 2 * q);
+            zc[JB][0] = z0 * dj.x;                                                           // D^-1 z feeds the next blocks
+            zc[JB][1] = z1 * dj.y;
+        }
+        lean_steps<NT, JB + 1, FWD>(load, Lsm, R, U, ok, logdet, want_logdet, r, q, lane, rhs, zc, zscr, dinv);
     }
 }
 
-// Solve L L^T x = rhs with the lean factor (same scheme as chol_solve)
+// Backward substitution L^T x = z with the lean factor; z = L^{-1} rhs was parked in `zscr` (8 NT doubles of shared
+// memory owned by this warp) by lean_steps<FWD>.  x is returned row-replicated: xr[I] = x[8 I + r] on every lane of row r.
 template <int NT>
 __device__ __forceinline__ void lean_solve(const double* __restrict__ Lsm, const double (&R)[Lean<NT>::RDIM][2],
-                                           const double (&U)[NT][2], const double* __restrict__ rhs, double (&xr)[NT], int r,
-                                           int q, int lane, double* __restrict__ zscr) {
-    {
-        double zc[NT][2];
-#pragma unroll
-        for (int jb = 0; jb < NT; ++jb) {
-            double acc = 0.0;
-#pragma unroll
-            for (int J = 0; J < jb; ++J) {
-                const double2 t = lean_tile<NT>(Lsm, R, jb, J, lane);
-                acc = fma(t.x, zc[J][0], fma(t.y, zc[J][1], acc));
-            }
-            double rr = rhs[8 * jb + r];
-            if (jb > 0) rr -= quadreduce(acc);
-            zc[jb][0] = colreduce(U[jb][0] * rr);
-            zc[jb][1] = colreduce(U[jb][1] * rr);
-            if (r == 0) *reinterpret_cast<double2*>(zscr + 8 * jb + 2 * q) = make_double2(zc[jb][0], zc[jb][1]);
-        }
-    }
+                                           const double (&U)[NT][2], const double* __restrict__ dinv, double (&xr)[NT], int r,
+                                           int q, int lane, const double* __restrict__ zscr) {
     __syncwarp();
 #pragma unroll
     for (int jb = NT - 1; jb >= 0; --jb) {
@@ -487,6 +418,8 @@ __device__ __forceinline__ void lean_solve(const double* __restrict__ Lsm, const
         const double2 z = *reinterpret_cast<const double2*>(zscr + 8 * jb + 2 * q);
         double z0 = z.x, z1 = z.y;
         if (jb < NT - 1) { z0 -= colreduce(c0); z1 -= colreduce(c1); }
+        const double2 dj = *reinterpret_cast<const double2*>(dinv + 8 * jb + 2 * q);
+        z0 *= dj.x; z1 *= dj.y;
         xr[jb] = quadreduce(fma(U[jb][0], z0, U[jb][1] * z1));
     }
     __syncwarp();
@@ -553,38 +486,35 @@ struct Pipe {
         bulk_g2s(stage0 + st * Lay<NT>::STAGE_D, Vt + (size_t)t0 * NT * 64, bytes, full + st);
     }
     // all threads; the staging area may have been used as scratch (generic proxy) since the last pass
-    __device__ __forceinline__ void begin(unsigned g0, int nprefetch) const {
+    __device__ __forceinline__ void begin(unsigned g0) const {
         __syncthreads();
         if (tid == 0) {
             fence_proxy_async();
-            for (int c = 0; c < nprefetch && c < nch; ++c) issue(c, g0 + c);
+            for (int c = 0; c < NSTAGE - 1 && c < nch; ++c) issue(c, g0 + c);
         }
-    }
-    // pair variant: chunks c and c+1 are consumed together; thread 0 first issues the two chunks whose stages were
-    // released by every warp in the previous pair iteration (c + NSTAGE - 2 and c + NSTAGE - 1); begin() must have
-    // prefetched NSTAGE - 2 chunks
-    __device__ __forceinline__ const double* wait2(int c, unsigned g0, const double*& second) const {
-        if (tid == 0) {
-#pragma unroll
-            for (int d = NSTAGE - 2; d < NSTAGE; ++d) {
-                const int cn = c + d;
-                if (cn < nch) {
-                    const unsigned gp = g0 + cn - NSTAGE;
-                    if (cn >= NSTAGE) mbar_wait(empty + gp % NSTAGE, (gp / NSTAGE) & 1);
-                    issue(cn, g0 + cn);
-                }
-            }
-        }
-        __syncwarp();
-        const unsigned g = g0 + c;
-        mbar_wait(full + g % NSTAGE, (g / NSTAGE) & 1);
-        if (c + 1 < nch) mbar_wait(full + (g + 1) % NSTAGE, ((g + 1) / NSTAGE) & 1);
-        second = stage0 + ((g + 1) % NSTAGE) * Lay<NT>::STAGE_D;
-        return stage0 + (g % NSTAGE) * Lay<NT>::STAGE_D;
     }
     // wait for chunk c of the pass; thread 0 first tops the pipeline up (the stage of chunk c-1 is refilled)
-    __device__ __forceinline__ const double* wait(int c, unsigned g0) const {
+    __device__ __forceinline__ const double* wait(int c, unsigned g0, long long* pf = nullptr) const {
         const unsigned g = g0 + c;
+#ifdef MX_TPROF
+        // diagnostics build: pf[0] time thread 0 waits for a free stage, pf[1] time it waits for data, pf[2] steps,
+        // pf[4] / pf[5] issue -> completion latency of the copies it had to wait for (sum / count); pf[8..] issue stamps
+        if (tid == 0 && pf) {
+            const long long t0 = clock64();
+            const int cn = c + NSTAGE - 1;
+            if (cn < nch) {
+                if (c >= 1) mbar_wait(empty + (g - 1) % NSTAGE, ((g - 1) / NSTAGE) & 1);
+                pf[0] += clock64() - t0;
+                issue(cn, g0 + cn);
+                pf[8 + (g0 + cn) % NSTAGE] = clock64();
+            }
+            const long long w0 = clock64();
+            mbar_wait(full + g % NSTAGE, (g / NSTAGE) & 1);
+            const long long w1 = clock64();
+            pf[1] += w1 - w0; pf[2] += 1;
+            if (w1 - w0 > 60 && c >= NSTAGE - 1) { pf[4] += w1 - pf[8 + g % NSTAGE]; pf[5] += 1; }
+        } else
+#endif
         if (tid == 0) {
             const int cn = c + NSTAGE - 1;
             if (cn < nch) {
@@ -603,8 +533,9 @@ struct Pipe {
     }
 };
 
-// H-pass body for one tile half: Z_owned += sum_k w_k V'[k, I] V'[k, J] over this warp's k-tiles, then the
-// two k-groups are added in a fixed order into Zfull (all NT x NT tiles, C layout, symmetric fill).
+// H-pass body for one tile half: Z_owned += sum_k w_k V'[k, I] V'[k, J] over this warp's k-tiles (two of every chunk:
+// k-group kg takes tiles 2 kg and 2 kg + 1), then the k-groups are added in a fixed order into Zfull (all NT x NT
+// tiles, C layout, symmetric fill).
 template <int NT, int TH>
 __device__ __forceinline__ void hpass_body(const Pipe<NT>& pipe, unsigned g0, const double* __restrict__ wrow, int kg,
                                            int lane, int r, int q, int offY0, int offY1, double* __restrict__ Zf) {
@@ -617,61 +548,77 @@ __device__ __forceinline__ void hpass_body(const Pipe<NT>& pipe, unsigned g0, co
 #pragma unroll
             for (int J = 0; J <= I; ++J) { zacc[tri(I, J)][0] = 0.0; zacc[tri(I, J)][1] = 0.0; }
         }
-    // this warp handles k-tile (c*CH + kg) of every chunk; w is prefetched two chunks ahead
-    static_assert(CH == NWARP / 2, "one k-tile of every chunk per k-group");
+    static_assert(CH == 2 * NKG, "two k-tiles of every chunk per k-group");
+    // w of this lane's two omega rows (2q, 2q+1) of both tiles, prefetched one chunk ahead (the scratch rows live in
+    // L2: the load must not sit between the arrival of a chunk and its first MMA)
     auto loadw = [&](int kt) -> double2 {
         if (kt < n_kt) return *reinterpret_cast<const double2*>(wrow + kt * 8 + 2 * q);
         return make_double2(0.0, 0.0);
     };
-    double2 w0 = loadw(kg), w1 = loadw(CH + kg);
+    double2 wa = loadw(2 * kg), wb = loadw(2 * kg + 1);
     for (int c = 0; c < nch; ++c) {
         const double* stage = pipe.wait(c, g0);
-        const double2 w2 = loadw((c + 2) * CH + kg);
-        const int kt = c * CH + kg;
-        if (kt < n_kt) hpass_ktile<NT, TH>(stage + kg * NT * 64, w0.x, w0.y, offY0, offY1, zacc);
-        w0 = w1; w1 = w2;
+        const int kt = c * CH + 2 * kg;
+        const double2 na = loadw(kt + CH), nb = loadw(kt + CH + 1);
+        if (kt < n_kt) hpass_ktile<NT, TH>(stage + (2 * kg) * NT * 64, wa.x, wa.y, offY0, offY1, zacc);
+        if (kt + 1 < n_kt) hpass_ktile<NT, TH>(stage + (2 * kg + 1) * NT * 64, wb.x, wb.y, offY0, offY1, zacc);
+        wa = na; wb = nb;
         pipe.release(c, g0);
     }
+    // The k-groups are added in the fixed order ((g0 + g1) + g2) + ... (deterministic sums).  Groups 1.. park their
+    // partial tiles behind Zfull -- the staging ring, J and the trial vectors are all dead during an H-pass and
+    // contiguous -- and the two warps of group 0 finish the sum, write Zfull and mirror it.
+    double* const slots = Zf + NT * NT * 64;
     __syncthreads();                                       // every warp is done with the staging area
-    // the k-groups add their partial tiles in a fixed order (deterministic sums); the last one mirrors
-#pragma unroll 1
-    for (int g = 0; g < CH; ++g) {
-        if (kg == g) {
+    if (kg > 0) {
 #pragma unroll
-            for (int I = 0; I < NT; ++I)
-                if (owns<NT, TH>(I)) {
+        for (int I = 0; I < NT; ++I)
+            if (owns<NT, TH>(I)) {
 #pragma unroll
-                    for (int J = 0; J <= I; ++J) {
-                        double2* p = reinterpret_cast<double2*>(Zf + (I * NT + J) * 64 + 2 * lane);
-                        double2 vv = make_double2(zacc[tri(I, J)][0], zacc[tri(I, J)][1]);
-                        if (g > 0) { const double2 o = *p; vv.x += o.x; vv.y += o.y; }
-                        *p = vv;
-                        if (g == CH - 1 && I != J) {       // mirror: tile (J, I) = transpose
-                            Zf[(J * NT + I) * 64 + (2 * q) * 8 + r] = vv.x;
-                            Zf[(J * NT + I) * 64 + (2 * q + 1) * 8 + r] = vv.y;
-                        }
+                for (int J = 0; J <= I; ++J)
+                    *reinterpret_cast<double2*>(slots + ((kg - 1) * NTRI + tri(I, J)) * 64 + 2 * lane) =
+                        make_double2(zacc[tri(I, J)][0], zacc[tri(I, J)][1]);
+            }
+    }
+    __syncthreads();
+    if (kg == 0) {
+#pragma unroll
+        for (int I = 0; I < NT; ++I)
+            if (owns<NT, TH>(I)) {
+#pragma unroll
+                for (int J = 0; J <= I; ++J) {
+                    double2 vv = make_double2(zacc[tri(I, J)][0], zacc[tri(I, J)][1]);
+#pragma unroll
+                    for (int g = 0; g < NKG - 1; ++g) {
+                        const double2 o = *reinterpret_cast<const double2*>(slots + (g * NTRI + tri(I, J)) * 64 + 2 * lane);
+                        vv.x += o.x; vv.y += o.y;
+                    }
+                    *reinterpret_cast<double2*>(Zf + (I * NT + J) * 64 + 2 * lane) = vv;
+                    if (I != J) {                          // mirror: tile (J, I) = transpose
+                        Zf[(J * NT + I) * 64 + (2 * q) * 8 + r] = vv.x;
+                        Zf[(J * NT + I) * 64 + (2 * q + 1) * 8 + r] = vv.y;
                     }
                 }
-        }
-        __syncthreads();
+            }
     }
+    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
+// CTAs per SM the instantiation is compiled for: the target (MX_CTAS_PER_SM), or what its shared memory allows
 template <int NT>
-__global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const SweepArgs a) {
+__host__ __device__ constexpr int ctas_per_sm() {
+    int n = (228 * 1024) / (Lay<NT>::total * (int)sizeof(double) + 1024);
+    if (n > MX_CTAS_PER_SM) n = MX_CTAS_PER_SM;
+    return n < 1 ? 1 : n;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const SweepArgs a) {
     using LY = Lay<NT>;
-    // NT <= 7: two CTAs per SM at 128 registers per thread, all eight warps factorise with the lean Cholesky;
-    // NT == 8: two CTAs per SM, four solver warps are lent the other warp group's registers (setmaxnreg) for the
-    // register-resident Cholesky; NT > 8: one CTA per SM (shared memory), every thread owns 255 registers
-    constexpr bool LEAN = NT <= 7;
-    constexpr bool REGSPLIT = NT == 8;
     using LN = Lean<NT>;
-    static_assert(!LEAN || NT * NT * 64 + 5 * LN::NSMT * 64 <= LY::NST * LY::STAGE_D,
-                  "the parked tiles of warps 0-4 must not overlap Zfull (warp 0 factorises while Zfull is live)");
-    static_assert(!LEAN || NWARP * LN::NSMT * 64 <= LY::NST * LY::STAGE_D, "parked tiles must fit in the staging area");
     constexpr int SP = LY::SP;
     constexpr int NTRI = LY::NTRI;
     extern __shared__ __align__(128) double sm[];
@@ -712,33 +659,22 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
     // for them: MxSweepOut.phase_cycles)
     const bool timing = a.o_phase != nullptr;
     auto tick = [&](int k) {
+#ifndef MX_TPROF
         if (timing && tid == 0) { const long long t = clock64(); ctl.tph[k] += t - ctl.t_last; ctl.t_last = t; }
+#else
+        (void)k;
+#endif
     };
     const uint64_t keep_pol = l2_evict_last_policy();
 
-    // Register hand-over around a solver phase.  Every thread calls both; between them only warps < NSOLVE work,
-    // the others go straight to the closing barrier.
-    auto regs_to_solvers = [&]() {
-        if constexpr (REGSPLIT) {
-            if (warp < NSOLVE) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(REG_HI));
-            else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(REG_LO));
-        }
-    };
-    auto regs_back = [&]() {                              // ends with a CTA barrier
-        if constexpr (REGSPLIT) {
-            if (warp < NSOLVE) { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(REG_EVEN)); __syncthreads(); }
-            else { __syncthreads(); asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(REG_EVEN)); }
-        } else {
-            __syncthreads();
-        }
-    };
-
     // ---- T-pass: evaluate the cost function at the trial vectors tb[0..7] ---------------------------
     // Per unique trial u < nuniq: yb[u], uchi2, uS, uQ, and w (and H) rows in scratch.
+    // Warp w works on k-tile (NWARP c + w) of chunk c: x = V' t for the eight trials (M of the MMA), the pointwise map
+    // H = D e^x with its entropy terms, y += H^T V'.
     auto tpass = [&]() {
         const unsigned g0 = ctl.gchunk;
         const int nuniq = ctl.nuniq;
-        pipe.begin(g0, LY::NST - 2);
+        pipe.begin(g0);
         double tA[NT][2];
 #pragma unroll
         for (int jt = 0; jt < NT; ++jt) {
@@ -752,14 +688,26 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
         const bool live = r < nuniq;
         double* const wrow = wscr + (size_t)(live ? ctl.urow[r] : 0) * rowlen;
         double* const hrow = hscr + (size_t)(live ? ctl.urow[r] : 0) * rowlen;
-        // two chunks per iteration: warps 0-3 take the four k-tiles of chunk c, warps 4-7 those of chunk c+1
-        const int half = warp >> 2, wq = warp & 3;
-        for (int c = 0; c < nch; c += 2) {
-            const double* stB;
-            const double* stA = pipe.wait2(c, g0, stB);
-            const int kt = (c + half) * CH + wq;
+        // D of this lane's two omega rows, fetched one step ahead (it may come from L2)
+        auto loadD = [&](int kt) -> double2 {
+            const int k0 = kt * 8 + 2 * q;
+            double2 Dv = make_double2(0.0, 0.0);
+            if (kt < n_kt) {
+                if (k0 + 1 < a.n_omega) Dv = *reinterpret_cast<const double2*>(Dsp + k0);
+                else if (k0 < a.n_omega) Dv.x = Dsp[k0];
+            }
+            return Dv;
+        };
+        double2 Dv = loadD(warp);
+        for (int c = 0; c < nch; ++c) {
+#ifdef MX_TPROF
+            const double* tile = pipe.wait(c, g0, timing ? ctl.pf : nullptr) + warp * NT * 64;
+#else
+            const double* tile = pipe.wait(c, g0) + warp * NT * 64;
+#endif
+            const int kt = c * CH + warp;
             const bool valid = kt < n_kt;
-            const double* tile = ((half && valid) ? stB : stA) + wq * NT * 64;
+            const double2 Dn = loadD(kt + CH);
             double C0[2] = {0.0, 0.0}, C1[2] = {0.0, 0.0};
 #pragma unroll
             for (int jt = 0; jt < NT; ++jt) {
@@ -769,11 +717,6 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
             }
             double Hv[2], Wv[2];
             const int k0 = kt * 8 + 2 * q;
-            double2 Dv = make_double2(0.0, 0.0);
-            if (valid) {
-                if (k0 + 1 < a.n_omega) Dv = *reinterpret_cast<const double2*>(Dsp + k0);
-                else if (k0 < a.n_omega) Dv.x = Dsp[k0];
-            }
             // the two (plus-minus: four) exponentials of this lane as independent straight-line chains; the rare
             // huge arguments (overflowing pump trials) take the library path
             const double x0 = C0[0] + C1[0], x1 = C0[1] + C1[1];
@@ -813,14 +756,16 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                 st_keep_v2(wrow + k0, Wv[0], Wv[1], keep_pol);
                 if (pm) st_keep_v2(hrow + k0, Hv[0], Hv[1], keep_pol);
             }
+            if (valid) {
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int off = e ? offY1 : offY0;
+                for (int e = 0; e < 2; ++e) {
+                    const int off = e ? offY1 : offY0;
 #pragma unroll
-                for (int jt = 0; jt < NT; ++jt) dmma(yacc[jt], Hv[e], tile[jt * 64 + off]);
+                    for (int jt = 0; jt < NT; ++jt) dmma(yacc[jt], Hv[e], tile[jt * 64 + off]);
+                }
             }
+            Dv = Dn;
             pipe.release(c, g0);
-            if (c + 1 < nch) pipe.release(c + 1, g0);
         }
         __syncthreads();                                   // staging area is free: reuse as yred[NWARP][8][SP]
         if (tid == 0) ctl.gchunk = g0 + nch;
@@ -833,12 +778,12 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
             if (q == 0) sm[LY::o_sred + warp * 8 + r] = sq;
         }
         __syncthreads();
-        static_assert(NWARP == 8, "fixed-order reduction tree over eight warps");
-        for (int i = tid; i < MAXB * SP; i += NTHR) {
+        for (int i = tid; i < MAXB * SP; i += NTHR) {      // fixed-order tree over the warps (deterministic sums)
             const int b = i / SP, j = i - b * SP;
             const double* y0 = yred + b * SP + j;
-            sm[LY::o_yb + i] = ((y0[0 * 8 * SP] + y0[1 * 8 * SP]) + (y0[2 * 8 * SP] + y0[3 * 8 * SP])) +
-                               ((y0[4 * 8 * SP] + y0[5 * 8 * SP]) + (y0[6 * 8 * SP] + y0[7 * 8 * SP]));
+            double t = (y0[0 * 8 * SP] + y0[1 * 8 * SP]) + (y0[2 * 8 * SP] + y0[3 * 8 * SP]);
+            if constexpr (NWARP == 8) t += (y0[4 * 8 * SP] + y0[5 * 8 * SP]) + (y0[6 * 8 * SP] + y0[7 * 8 * SP]);
+            sm[LY::o_yb + i] = t;
         }
         __syncthreads();
         for (int u = warp; u < nuniq; u += NWARP) {        // chi2 = |Xi y - g~|^2 + c0  (functions.py:358-360 in singular space)
@@ -849,7 +794,8 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
             }
             c2 = warp_sum(c2) + ctl.c0;
             const double* sr = sm + LY::o_sred + u;
-            const double S = ((sr[0] + sr[8]) + (sr[16] + sr[24])) + ((sr[32] + sr[40]) + (sr[48] + sr[56]));
+            double S = (sr[0] + sr[8]) + (sr[16] + sr[24]);
+            if constexpr (NWARP == 8) S += (sr[32] + sr[40]) + (sr[48] + sr[56]);
             if (lane == 0) {
                 ctl.uchi2[u] = c2; ctl.uS[u] = S;
                 ctl.uQ[u] = ctl.ufail[u] ? nan("") : 0.5 * c2 * a.eta - ctl.alpha * S;   // maxent_cost_function.py:82
@@ -861,7 +807,7 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
     // ---- H-pass: Z = V'^T diag(w) V' with w from scratch row `row` -> Zfull (all NT x NT tiles, C layout) ----
     auto hpass = [&](int row) {
         const unsigned g0 = ctl.gchunk;
-        pipe.begin(g0, LY::NST - 1);
+        pipe.begin(g0);
         const int kg = warp >> 1, th = warp & 1;
         const double* wrow = wscr + (size_t)row * rowlen;
         double* Zf = sm + LY::o_stage;
@@ -879,9 +825,12 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
             const double rr = xi * sm[LY::o_ycur + i] - sm[LY::o_gt + i];
             const double u = (i < s) ? a.eta * xi * rr + alpha * sm[LY::o_v + i] : 0.0;
             sm[LY::o_u + i] = u;
-            if (bryan) {      // f = g + alpha v ; (eta Lambda Z + mu) dv = f  <=>  (eta Z + mu/Lambda) dv = f/Lambda
+            if (bryan) {
+                // f = g + alpha v ; the reference solves the non-symmetric (eta Lambda Z + mu) dv = f
+                // (bryan_cost_function.py:114-128).  With Lambda = Xi^2 the matrix is similar to the symmetric, well
+                // scaled M = eta Xi Z Xi:  (M + mu) w = f / xi ,  dv = xi w  -- same eigenvalues, uniform shift
                 sm[LY::o_f + i] = u;
-                sm[LY::o_rhs + i] = (i < s) ? u / sm[LY::o_lam + i] : 0.0;
+                sm[LY::o_rhs + i] = (i < s) ? u / xi : 0.0;
             }
         }
         __syncthreads();
@@ -928,8 +877,10 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                 }
                 c[0] = fma(a.eta, c[0], alpha * zij.x);       // maxent_cost_function.py:161-162 in singular space
                 c[1] = fma(a.eta, c[1], alpha * zij.y);
-            } else {
-                c[0] = a.eta * zij.x; c[1] = a.eta * zij.y;
+            } else {                                           // M = eta Xi Z Xi
+                const double xr_ = a.eta * sm[LY::o_xi + 8 * I + r];
+                const double2 xc = *reinterpret_cast<const double2*>(sm + LY::o_xi + 8 * J + 2 * q);
+                c[0] = xr_ * zij.x * xc.x; c[1] = xr_ * zij.y * xc.y;
             }
             if (I == J) {                                      // padded rows/columns: identity
                 const int i0 = 8 * I + r;
@@ -947,11 +898,11 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
         if (warp == 0) {
             // floor for the planner's equivalence pre-test: two dampings can only give the same shifted diagonal
             // if they differ by less than ~2 ulps of min_k |J_kk| / (d shift_k / d mu) + mu, where the shift of entry k
-            // is mu (Normal / PlusMinus), mu / Lambda_k (Bryan) or mu J_kk (Marquardt)
+            // is mu (all three cost functions; Bryan works on the symmetrised matrix) or mu J_kk (Marquardt)
             double m = INFINITY;
             for (int k = lane; k < s; k += 32) {
                 const double jd = fabs(sm[LY::o_jd + k]);
-                m = fmin(m, a.marquardt ? 1.0 : (bryan ? jd * sm[LY::o_lam + k] : jd));
+                m = fmin(m, a.marquardt ? 1.0 : jd);
             }
             m = -warp_max(-m);
             if (lane == 0) ctl.jdmin = m;
@@ -959,95 +910,55 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
         __syncthreads();
     };
 
-    // damping of diagonal entry i: mu * 1 (Bryan: the system is divided by Lambda), or -- Marquardt's variant,
-    // levenberg_minimizer.py:181-185 -- mu * diag(J): J_ii + mu * J_ii, which for Bryan is again row i of
-    // (eta Lambda Z + mu diag(eta Lambda Z)) divided by Lambda_i
+    // damping of diagonal entry i: mu * 1, or -- Marquardt's variant, levenberg_minimizer.py:181-185 -- mu * diag(J):
+    // J_ii + mu * J_ii (for Bryan diag(eta Lambda Z) = diag(eta Xi Z Xi), so the symmetrised system carries the same shift)
     const bool marq = a.marquardt != 0;
     auto shift_of = [&](int i, double mu) -> double {
-        return marq ? mu * sm[LY::o_jd + i] : (bryan ? mu / sm[LY::o_lam + i] : mu);
+        return marq ? mu * sm[LY::o_jd + i] : mu;
     };
 
     // ---- P3: factorise J + shift(mu_u) and solve for every unique trial (one solver warp per matrix) -------
     auto solve_trials = [&]() {
         const int nuniq = ctl.nuniq;
-        if constexpr (LEAN) {
-            // every warp factorises one shifted Hessian: eight trials per round
-            double* const Lsm = sm + LY::o_stage + LY::NST * LY::STAGE_D - (warp + 1) * LN::NSMT * 64;
-            for (int u = warp; u < nuniq; u += NWARP) {
-                const double mu = ctl.umu[u];
-                auto load = [&](int I, int J) -> double2 {
-                    double2 v = *reinterpret_cast<const double2*>(sm + LY::o_J + tri(I, J) * 64 + 2 * lane);
-                    if (I == J) {
-                        const int i0 = 8 * I + r;
-                        if (i0 < s) {
-                            const double sh = shift_of(i0, mu);
-                            if (r == 2 * q) v.x += sh;
-                            if (r == 2 * q + 1) v.y += sh;
-                        }
-                    }
-                    return v;
-                };
-                double R[LN::RDIM][2];
-                double U[NT][2];
-                bool ok = true;
-                double ld = 0.0;
-                lean_steps<NT, 0>(load, Lsm, R, U, ok, ld, false, r, q, lane);
-                ok = __all_sync(0xffffffffu, ok);
-                double xr[NT];
-                lean_solve<NT>(Lsm, R, U, sm + LY::o_rhs, xr, r, q, lane, sm + LY::o_dvb + u * SP);
-                if (q == 0) {
-#pragma unroll
-                    for (int I = 0; I < NT; ++I) {
-                        const int i0 = 8 * I + r;
-                        const double dv = ok ? xr[I] : 0.0;
-                        sm[LY::o_dvb + u * SP + i0] = dv;
-                        sm[LY::o_tb + u * SP + i0] = ok ? sm[LY::o_v + i0] - dv : 0.0;
-                    }
-                }
-                if (lane == 0) ctl.ufail[u] = ok ? 0 : 1;
-            }
-            __syncthreads();
-            return;
-        }
-        regs_to_solvers();
-        if (warp < NSOLVE) {
-            for (int u = warp; u < nuniq; u += NSOLVE) {
-                const double mu = ctl.umu[u];
-                double A[NTRI][2];
-#pragma unroll
-                for (int t = 0; t < NTRI; ++t) {
-                    const double2 v = *reinterpret_cast<const double2*>(sm + LY::o_J + t * 64 + 2 * lane);
-                    A[t][0] = v.x; A[t][1] = v.y;
-                }
-#pragma unroll
-                for (int I = 0; I < NT; ++I) {
+        // every warp factorises one shifted Hessian at a time (NWARP trials per round); the strictly-lower tiles of
+        // the leading block columns are parked in this warp's slice of the idle staging ring
+        double* const Lsm = sm + LY::o_stage + LY::NST * LY::STAGE_D - (warp + 1) * LN::NSMT * 64;
+        for (int u = warp; u < nuniq; u += NWARP) {
+            const double mu = ctl.umu[u];
+            auto load = [&](int I, int J) -> double2 {
+                double2 v = *reinterpret_cast<const double2*>(sm + LY::o_J + tri(I, J) * 64 + 2 * lane);
+                if (I == J) {
                     const int i0 = 8 * I + r;
                     if (i0 < s) {
                         const double sh = shift_of(i0, mu);
-                        if (r == 2 * q) A[tri(I, I)][0] += sh;
-                        if (r == 2 * q + 1) A[tri(I, I)][1] += sh;
+                        if (r == 2 * q) v.x += sh;
+                        if (r == 2 * q + 1) v.y += sh;
                     }
                 }
-                double U[NT][2];
-                bool ok = true;
-                double ld = 0.0;
-                chol_steps<NT, 0>(A, U, ok, ld, false, r, q, lane);
-                ok = __all_sync(0xffffffffu, ok);
-                double xr[NT];
-                chol_solve<NT>(A, U, sm + LY::o_rhs, xr, r, q, sm + LY::o_dvb + u * SP);
-                if (q == 0) {
+                return v;
+            };
+            double R[LN::RDIM][2];
+            double U[NT][2];
+            bool ok = true;
+            double ld = 0.0;
+            double zc[NT][2];
+            double* const trow = sm + LY::o_tb + u * SP;          // scratch for the forward substitution, then t = v - dv
+            double* const dinv = sm + LY::o_yb + u * SP;          // 1 / d of the L D L^T factorisation (yb is dead here)
+            lean_steps<NT, 0, true>(load, Lsm, R, U, ok, ld, false, r, q, lane, sm + LY::o_rhs, zc, trow, dinv);
+            ok = __all_sync(0xffffffffu, ok);
+            double xr[NT];
+            lean_solve<NT>(Lsm, R, U, dinv, xr, r, q, lane, trow);
+            if (q == 0) {
 #pragma unroll
-                    for (int I = 0; I < NT; ++I) {
-                        const int i0 = 8 * I + r;
-                        const double dv = ok ? xr[I] : 0.0;
-                        sm[LY::o_dvb + u * SP + i0] = dv;
-                        sm[LY::o_tb + u * SP + i0] = ok ? sm[LY::o_v + i0] - dv : 0.0;
-                    }
+                for (int I = 0; I < NT; ++I) {
+                    const int i0 = 8 * I + r;
+                    const double dv = bryan ? sm[LY::o_xi + i0] * xr[I] : xr[I];
+                    trow[i0] = ok ? sm[LY::o_v + i0] - dv : 0.0;
                 }
-                if (lane == 0) ctl.ufail[u] = ok ? 0 : 1;
             }
+            if (lane == 0) ctl.ufail[u] = ok ? 0 : 1;
         }
-        regs_back();
+        __syncthreads();
     };
 
     // ---- log det(I + eta Xi Z Xi / alpha) by warp 0 (probabilities.py:76-85 via Sylvester) -----------------
@@ -1068,22 +979,10 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
         double U[NT][2];
         bool ok = true;
         double ld = 0.0;
-        if constexpr (LEAN) {
-            double* const Lsm = sm + LY::o_stage + LY::NST * LY::STAGE_D - LN::NSMT * 64;     // warp 0's slice, beyond Zfull
-            double R[LN::RDIM][2];
-            lean_steps<NT, 0>(entry, Lsm, R, U, ok, ld, true, r, q, lane);
-        } else {
-            double A[NTRI][2];
-#pragma unroll
-            for (int I = 0; I < NT; ++I) {
-#pragma unroll
-                for (int J = 0; J <= I; ++J) {
-                    const double2 m = entry(I, J);
-                    A[tri(I, J)][0] = m.x; A[tri(I, J)][1] = m.y;
-                }
-            }
-            chol_steps<NT, 0>(A, U, ok, ld, true, r, q, lane);
-        }
+        double* const Lsm = sm + LY::o_J;                  // J of the finished iteration is dead: park the tiles there
+        double R[LN::RDIM][2];
+        double zc[NT][2];
+        lean_steps<NT, 0, false>(entry, Lsm, R, U, ok, ld, true, r, q, lane, nullptr, zc, nullptr, sm + LY::o_yb);
         ok = __all_sync(0xffffffffu, ok);
         return ok ? ld : nan("");
     };
@@ -1117,6 +1016,9 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
         __syncthreads();
         // first evaluation at v0 (the reference's func_val = function(v), levenberg_minimizer.py:150)
         if (timing && tid == 0) { ctl.t_last = clock64(); for (int k = 0; k < 8; ++k) ctl.tph[k] = 0; }
+#ifdef MX_TPROF
+        if (timing && tid == 0) for (int k = 0; k < 16; ++k) ctl.pf[k] = 0;
+#endif
         tpass();
         tick(PHT_TPASS);
         for (int i = tid; i < SP; i += NTHR) sm[LY::o_ycur + i] = sm[LY::o_yb + i];
@@ -1146,13 +1048,12 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                 if (!ctl.action) break;
                 // ---- this alpha is finished: probability, outputs ----
                 const size_t o = (size_t)sp * a.n_alpha + ctl.ia;
-                if (a.want_prob) {                             // the factorisation needs the solver register budget
-                    regs_to_solvers();
+                if (a.want_prob) {
                     if (warp == 0) {
                         const double ld = logdet_prob();
                         if (lane == 0) ctl.pq[0] = ld;
                     }
-                    regs_back();
+                    __syncthreads();
                 }
                 if (tid == 0) {
                     const double logp = a.want_prob ? -0.5 * ctl.pq[0] - ctl.lm.Q1 - log(ctl.alpha) : nan("");
@@ -1186,7 +1087,11 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                 if (ctl.ia >= a.n_alpha) {
                     if (timing && tid == 0) {
                         tick(PHT_OTHER);
+#ifdef MX_TPROF
+                        for (int k = 0; k < 8; ++k) a.o_phase[(size_t)sp * 8 + k] = ctl.pf[k];
+#else
                         for (int k = 0; k < 8; ++k) a.o_phase[(size_t)sp * 8 + k] = ctl.tph[k];
+#endif
                     }
                     spectrum_done = true;
                     break;
@@ -1257,7 +1162,7 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                         const int live = (L.phase == PH_WALK) ? L.dvnew : (L.phase == PH_PROBE ? L.dv : ID_NONE);
                         if (live >= 0 && live < MAXB) {
                             for (int i = lane; i < SP; i += 32) {
-                                sm[LY::o_cdv + i] = sm[LY::o_dvb + live * SP + i];
+                                sm[LY::o_ctb + i] = sm[LY::o_tb + live * SP + i];
                                 sm[LY::o_cy + i] = sm[LY::o_yb + live * SP + i];
                             }
                             const double lmu = shfl(u_mu, live), lQ = shfl(u_Q, live);
@@ -1385,6 +1290,16 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
                             ctl.ufail[lane] = 0;
                         }
                         if (lane == 0) { ctl.nb = np; ctl.nuniq = npu; ctl.ntrial += npu; ctl.nbatch += 1; }
+#ifdef MX_PLANPROF
+                        // diagnostics: charge the planning time to slot 0 (fast paths) or 6 (generic planner); slot 4
+                        // counts generic plans, slot 5 fast plans
+                        if (timing && lane == 0) {
+                            const long long t = clock64();
+                            ctl.tph[fast ? 0 : 6] += t - ctl.t_last; ctl.t_last = t;
+                            ctl.ntrial -= npu;                  // n_trial output = number of generic plans, by phase
+                            ctl.ntrial += fast ? 0 : (L.phase == PH_FIRST ? 1 : L.phase == PH_PUMP ? 1000 : L.phase == PH_PROBE ? 1000000 : 100000000);
+                        }
+#endif
                     }
                     if (lane == 0) { ctl.lm = L; ctl.ns = ns; ctl.nq = nq; ctl.conv = done; }
                 }
@@ -1411,10 +1326,13 @@ __global__ void __launch_bounds__(NTHR, (NT <= 8 ? 2 : 1)) sweep2_kernel(const S
             // ---- accept: v -= dv ; the accepted trial becomes the current point (levenberg_minimizer.py:239-243) ----
             {
                 const int id = ctl.lm.dv;
-                const double* dv = (id == ID_CARRY) ? sm + LY::o_cdv : sm + LY::o_dvb + id * SP;
+                // the accepted trial vector t = v - dv IS the new v (same subtraction, same operands); a failed solve has
+                // dv = 0 by definition
+                const double* tt = (id == ID_CARRY) ? sm + LY::o_ctb : sm + LY::o_tb + id * SP;
                 const double* yy = (id == ID_CARRY) ? sm + LY::o_cy : sm + LY::o_yb + id * SP;
+                const bool moved = ctl.ufail[id] == 0;
                 for (int i = tid; i < SP; i += NTHR) {
-                    if (i < s) sm[LY::o_v + i] -= dv[i];
+                    if (i < s && moved) sm[LY::o_v + i] = tt[i];
                     sm[LY::o_ycur + i] = yy[i];
                 }
                 __syncthreads();
@@ -1438,22 +1356,34 @@ template <int NT>
 int launch_sweep2(const SweepArgs& a, cudaStream_t stream, bool query, int* o_smem, int* o_grid) {
     const size_t bytes = (size_t)Lay<NT>::total * sizeof(double);
     if (o_smem) *o_smem = (int)bytes;
+    if (query && !o_grid) return MX_OK;                        // pure introspection: no device needed
     int dev = 0, sms = 0;
-    if (!query || o_grid) {
-        if (cudaGetDevice(&dev) != cudaSuccess) { if (query) { if (o_grid) *o_grid = 0; return MX_OK; } return MX_ERR_NO_DEVICE; }
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaGetDevice(&dev) != cudaSuccess) { if (query) { *o_grid = 0; return MX_OK; } return MX_ERR_NO_DEVICE; }
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaFuncSetAttribute(sweep2_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+        if (query) { cudaGetLastError(); if (o_grid) *o_grid = 0; return MX_OK; }
+        return MX_ERR_CUDA;
     }
-    int per_sm = (NT <= 8) ? 2 : 1;
-    if (const char* e = getenv("MX_CTAS_PER_SM")) { if (e[0] == '1') per_sm = 1; }     // diagnostics: uncontended phase times
+    // persistent CTAs: as many as are resident at once (registers and shared memory decide; ctas_per_sm<NT>() is what
+    // the instantiation was compiled for)
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep2_kernel<NT>, NTHR, bytes) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 1;
+    }
+    if (const char* e = getenv("MX_MAX_CTAS_PER_SM")) {        // diagnostics: uncontended phase times
+        const int cap = atoi(e);
+        if (cap >= 1 && cap < per_sm) per_sm = cap;
+    }
     int grid = per_sm * sms;
     if (grid > a.B) grid = a.B;
     if (grid < 1) grid = 1;
     if (o_grid) *o_grid = grid;
     if (query) return MX_OK;
-    cudaError_t e = cudaFuncSetAttribute(sweep2_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e != cudaSuccess) return MX_ERR_CUDA;
     sweep2_kernel<NT><<<grid, NTHR, bytes, stream>>>(a);
     return cudaGetLastError() == cudaSuccess ? MX_OK : MX_ERR_CUDA;
 }
+
+constexpr int threads_per_cta() { return NTHR; }
 
 }  // namespace mx2

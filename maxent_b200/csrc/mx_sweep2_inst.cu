@@ -6,4 +6,7 @@ namespace mx2 {
 int MX_CAT(sweep2_nt, MX_NT)(const mx::SweepArgs& a, cudaStream_t stream, bool query, int* o_smem, int* o_grid) {
     return launch_sweep2<MX_NT>(a, stream, query, o_smem, o_grid);
 }
+#if MX_NT == 7
+int sweep2_threads() { return threads_per_cta(); }
+#endif
 }  // namespace mx2

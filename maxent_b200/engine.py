@@ -86,10 +86,16 @@ class SharedProblem(object):
             self.n_sv_requested = int((S >= thr).sum())
             thr = max(thr, float(rank_floor) * float(S[0]))
             keep = torch.nonzero(S >= thr).flatten()
-            cap = _lib.MX_MAX_NSV if max_nsv is None else max_nsv
             self.n_sv_uncapped = int(keep.numel())
-            if keep.numel() > cap:
-                keep = keep[:cap]
+            if max_nsv is not None and keep.numel() > int(max_nsv):
+                keep = keep[:int(max_nsv)]               # explicit request of the caller: continue in a smaller space
+            if keep.numel() > _lib.MX_MAX_NSV:
+                # the reference keeps every S >= threshold (python/kernels.py:101-122); silently continuing in a
+                # truncated space would return a different A(omega), so this is an error, not a fallback
+                raise _lib.MaxEntLibraryError(
+                    "the kernel keeps %d singular values >= %g (numerical rank floor %g * S[0]); the fused path supports "
+                    "n_sv <= %d -- raise reduce_singular_space, or pass max_nsv=%d to truncate explicitly"
+                    % (keep.numel(), thr, rank_floor, _lib.MX_MAX_NSV, _lib.MX_MAX_NSV))
             U, S, V = U[:, keep].contiguous(), S[keep].contiguous(), V[:, keep].contiguous()
             self.U, self.S, self.V = U, S, V
             s = int(S.numel())
@@ -103,12 +109,30 @@ class SharedProblem(object):
             else:
                 M = (sqrtw[:, None] * (K @ V)).contiguous()
                 Q, Xi, P = self._svd(M, svd)
+                # A covariance estimated from few samples (TauMaxEnt.set_cov drops its null space, python/tau_maxent.py:
+                # 253-288) leaves k = n_tau' < s rows: M = Q[k, k] Xi[k] P[s, k]^T has rank <= k, and the singular space
+                # the kernels work in shrinks to it (directions of V outside the row space of M do not enter chi2; the
+                # entropy pulls them to the default model, where v' = 0 keeps them).
+                k = int(Xi.numel())
+                if k < s:
+                    # Complete P to an orthonormal s x s rotation with zero singular values: the extra directions do
+                    # not enter chi2 (zero rows of Xi, zero columns of Q) but keep their entropy term, exactly as in the
+                    # reference, whose v lives in the full s-dimensional space of the unrotated kernel
+                    # (python/kernels.py:160-180 rotates U only).
+                    if variant == "bryan":
+                        raise NotImplementedError("BryanCostFunction with fewer data rows (%d) than singular values (%d): "
+                                                  "its Hessian is singular" % (k, s))
+                    Pc = torch.linalg.svd(P, full_matrices=True)[0][:, k:]
+                    P = torch.cat([P, Pc], dim=1).contiguous()
+                    Xi = torch.cat([Xi, torch.zeros(s - k, dtype=f64, device=dev)])
             # The left vectors of singular values near the rounding floor come out of a one-sided Jacobi (or any
             # SVD) with an orthogonality error ~ eps * S[0] / S[i]; chi2 = |Xi y - Q^T g|^2 + |(1 - Q Q^T) g|^2
             # needs Q^T Q = 1.  Two Gram-Schmidt passes in order of decreasing singular value leave the
             # well-determined columns untouched (to rounding) and move the others by an amount whose effect on
             # K H is ~ 1e-2 * S[i] -- far below the data error.
             Q = self._reorthonormalize(Q)
+            if Q.shape[1] < s:                                           # rank-deficient whitening: zero columns for Xi = 0
+                Q = torch.cat([Q, torch.zeros((Q.shape[0], s - Q.shape[1]), dtype=f64, device=dev)], dim=1)
             self.P = P
             self.Vp = V if P is None else (V @ P).contiguous()
             self.Q = Q.contiguous()

@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 import maxent_b200 as mb
+from oracle import maxent_oracle as mo
 from tests import gpu_common as gc
 
 pytestmark = pytest.mark.gpu
@@ -274,6 +275,52 @@ def test_covariance_vs_error_vector():
     # switching back to a plain error undoes the rotation
     t3.set_error(1e-4)
     assert t3.K._T is None and t3.K.K.shape == (len(g["tau"]), len(g["omega"]))
+
+
+def test_rank_deficient_covariance():
+    """A covariance matrix estimated from fewer samples than singular values: set_cov drops its null space
+    (python/tau_maxent.py:253-288), the rotated kernel keeps k < n_sv rows, v stays n_sv-dimensional
+    (python/kernels.py:160-180).  Oracle: the reference algorithm on the rotated problem with the rotated U."""
+    pr = mo.synthetic_problem(120, 60, beta=20.0, mu=0.5, sigma=2e-3, seed=11)
+    rng = np.random.RandomState(5)
+    n_tau, k = 120, 30
+    B = rng.randn(n_tau, k)
+    cov = 4e-6 * (B @ B.T) / k                                 # rank 30 < n_sv
+    e, v = np.linalg.eigh(cov)
+    keep = e >= 1e-14
+    assert keep.sum() == k
+    T = v[:, keep].T
+    G = pr["G"][0] if pr["G"].ndim == 2 else pr["G"]
+    tm = mb.TauMaxEnt(alpha_mesh=mb.LogAlphaMesh(0.5, 500, 6), reduce_singular_space=1e-9)
+    tm.set_verbosity(mb.VerbosityFlags.Quiet)
+    tm.omega = mb.DataOmegaMesh(pr["omega"])
+    tm.set_G_tau_data(pr["tau"], G)
+    tm.set_cov(cov)
+    res = tm.run()
+    n_sv = len(tm.K.S)
+    assert n_sv > k
+    U0, S0, V0 = mo.kernel_svd(pr["K"], 1e-9)
+    o = mo.maxent_loop(T @ pr["K"], T @ G, np.sqrt(e[keep]), pr["omega"], np.asarray(tm.alpha_mesh),
+                       svd=(T @ U0, S0, V0))
+    assert o["n_sv"] == n_sv
+    assert np.all(gc.rel_A(res.A, o["A"]) <= 1e-7), gc.rel_A(res.A, o["A"])
+    np.testing.assert_allclose(res.chi2, o["chi2"], rtol=1e-7)
+    for name in ('LineFitAnalyzer', 'Chi2CurvatureAnalyzer'):
+        assert res.analyzer_results[name]['alpha_index'] == o["analyzers"][name]["alpha_index"]
+
+
+def test_rank_above_the_fused_limit_raises():
+    """A kernel whose numerical rank exceeds MX_MAX_NSV is an error (the reference keeps every S >= threshold,
+    python/kernels.py:101-122; a silent truncation would change A), unless the caller asks for the truncation."""
+    from maxent_b200 import engine, _lib
+    rng = np.random.RandomState(2)
+    K = rng.randn(200, 100)
+    om = np.linspace(-5, 5, 100)
+    with pytest.raises(_lib.MaxEntLibraryError):
+        engine.SharedProblem(K, 1e-2, mo.flat_default_model(om), mo.omega_delta(om), reduce_singular_space=1e-14)
+    prob = engine.SharedProblem(K, 1e-2, mo.flat_default_model(om), mo.omega_delta(om), reduce_singular_space=1e-14,
+                                max_nsv=64)
+    assert prob.n_sv == 64 and prob.n_sv_uncapped == 100
 
 
 def test_threshold_skip_and_unsupported_combinations():

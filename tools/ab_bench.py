@@ -50,9 +50,9 @@ def child(lib, spectra, phases, out_npz, cost_function):
              n_iter=res.n_iter.cpu().numpy(), n_solve=res.n_solve.cpu().numpy(),
              A_pick=res.A_out[:, 0].cpu().numpy())
     if phases:
-        for per_sm in ("2", "1"):
-            os.environ["MX_CTAS_PER_SM"] = per_sm
-            n = spectra if per_sm == "2" else spectra // 2
+        for per_sm in ("full", "1"):
+            os.environ["MX_MAX_CTAS_PER_SM"] = "99" if per_sm == "full" else per_sm
+            n = spectra if per_sm == "full" else max(148, spectra // 4)
             for _ in range(2):
                 torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -70,7 +70,7 @@ def child(lib, spectra, phases, out_npz, cost_function):
             out["phases_%s_per_sm" % per_sm]["tpass_us_per_batch"] = round(float(cyc[:, 2].sum() / 1965.0 / nb), 2)
             out["phases_%s_per_sm" % per_sm]["solver_us_per_batch"] = round(float(cyc[:, 1].sum() / 1965.0 / nb), 2)
             out["phases_%s_per_sm" % per_sm]["spectra_per_s_timing_build"] = round(n / e0.elapsed_time(e1) * 1e3, 1)
-        os.environ.pop("MX_CTAS_PER_SM")
+        os.environ.pop("MX_MAX_CTAS_PER_SM")
     print("ABRESULT " + json.dumps(out), flush=True)
 
 

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-phase device time of the sweep kernel (MxSweepOut.phase_cycles, clock64 of thread 0 of every CTA) on a
-slice of the benchmark batch.  MX_CTAS_PER_SM=1 gives the uncontended phase times (one CTA per SM).
+slice of the benchmark batch.  MX_MAX_CTAS_PER_SM=1 gives the uncontended phase times (one CTA per SM).
 
     python tools/phase_times.py [spectra]
 """
@@ -21,7 +21,7 @@ Gd = G.cuda()
 names = ["planner", "solver", "T-pass", "H-pass", "gradient", "J assembly", "accept/convergence/output", "replay"]
 out = {}
 for per_sm in ("2", "1"):
-    os.environ["MX_CTAS_PER_SM"] = per_sm
+    os.environ["MX_MAX_CTAS_PER_SM"] = per_sm
     lm = engine.LMParams()
     n = B if per_sm == "2" else B // 2
     for _ in range(2):
