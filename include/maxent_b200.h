@@ -125,10 +125,21 @@ int mx_layout_V(const double* V, int32_t n_omega, int32_t n_sv, double* Vt, void
 int mx_tau_kernel(const double* tau, const double* omega, int32_t n_tau, int32_t n_omega,
                   double beta, double* K, void* stream);
 
-/* One-sided Jacobi SVD of K[m, n] (m >= n), replaces np.linalg.svd in KernelSVD.svd
- * (python/kernels.py:53-64).  U[m, n], S[n] (descending), V[n, n]; work = m*n doubles. */
+/* One-sided (Hestenes) Jacobi SVD of K[m, n] (m >= n), every column: replaces np.linalg.svd in KernelSVD.svd
+ * (python/kernels.py:53-64).  U[m, n], S[n] (descending), V[n, n]; work = m*n + n*n + n + 64 doubles.  One persistent
+ * cooperative kernel, convergence decided on the device; `sweeps_done` (host, may be NULL) is filled by a
+ * stream-ordered copy, i.e. valid once the caller has synchronised `stream`. */
 int mx_svd_jacobi(const double* K, int32_t m, int32_t n, double* U, double* S, double* V,
                   double* work, int32_t max_sweeps, int32_t* sweeps_done, void* stream);
+
+/* Truncated SVD: the leading p triplets of K[m, n] (any shape, p <= min(m, n)) by a random range finder followed by
+ * one-sided Jacobi on p columns (csrc/mx_svd.cu).  U[m, p], S[p] (descending), V[n, p].  Exact to rounding
+ * (|K - U S V^T| ~ eps * S[0]) whenever S[p-1] is at the rounding floor of K, i.e. whenever p exceeds the numerical rank:
+ * the caller checks S[p-1] <= ~1e-15 * S[0] and asks again with a larger p otherwise.  Only triplets above the
+ * caller's cut enter the MaxEnt loop (python/kernels.py:101-122).  work = mx_svd_truncated_work_doubles(m, n, p). */
+int64_t mx_svd_truncated_work_doubles(int32_t m, int32_t n, int32_t p);
+int mx_svd_truncated(const double* K, int32_t m, int32_t n, int32_t p, double* U, double* S, double* V,
+                     double* work, uint64_t seed, void* stream);
 
 /* Project the data of B spectra into the singular space:
  *   gt[b] = Qw^T G[b]  and  c0[b] = | sqrtw*G[b] - Qo gt[b] |^2

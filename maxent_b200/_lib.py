@@ -57,6 +57,9 @@ SYMBOLS = [
     ("mx_tau_kernel", ctypes.c_int, [c_dp, c_dp, ctypes.c_int32, ctypes.c_int32, ctypes.c_double, c_dp, c_dp]),
     ("mx_svd_jacobi", ctypes.c_int, [c_dp, ctypes.c_int32, ctypes.c_int32, c_dp, c_dp, c_dp, c_dp,
                                      ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), c_dp]),
+    ("mx_svd_truncated_work_doubles", ctypes.c_int64, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]),
+    ("mx_svd_truncated", ctypes.c_int, [c_dp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_dp, c_dp, c_dp, c_dp,
+                                        ctypes.c_uint64, c_dp]),
     ("mx_project_data", ctypes.c_int, [ctypes.POINTER(MxProblem), c_dp, ctypes.c_int32, c_dp, c_dp, c_dp]),
     ("mx_alpha_sweep", ctypes.c_int, [ctypes.POINTER(MxProblem), c_dp, c_dp, ctypes.c_int32,
                                       ctypes.POINTER(MxSweepOut), c_dp, ctypes.c_int64, c_dp]),

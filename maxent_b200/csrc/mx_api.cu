@@ -275,6 +275,17 @@ int mx_svd_jacobi(const double* K, int32_t m, int32_t n, double* U, double* S, d
     return svd_jacobi(K, m, n, U, S, V, work, max_sweeps, sweeps_done, (cudaStream_t)stream);
 }
 
+int64_t mx_svd_truncated_work_doubles(int32_t m, int32_t n, int32_t p) {
+    if (m < 1 || n < 1 || p < 1 || p > m || p > n) return MX_ERR_BAD_ARG;
+    return svd_truncated_work_doubles(m, n, p);
+}
+
+int mx_svd_truncated(const double* K, int32_t m, int32_t n, int32_t p, double* U, double* S, double* V, double* work,
+                     uint64_t seed, void* stream) {
+    if (!K || !U || !S || !V || !work || m < 1 || n < 1 || p < 1 || p > m || p > n) return MX_ERR_BAD_ARG;
+    return svd_truncated(K, m, n, p, U, S, V, work, seed, (cudaStream_t)stream);
+}
+
 int mx_project_data(const MxProblem* p, const double* G, int32_t B, double* gt, double* c0, void* stream) {
     if (B == 0) return MX_OK;
     if (!p || !G || !gt || !c0 || B < 0) return MX_ERR_BAD_ARG;

@@ -169,10 +169,16 @@ struct Lean {
 #ifndef MX_NST_EXTRA
 #define MX_NST_EXTRA 0
 #endif
+// warps that factorise at the same time: all of them up to 7 tiles; beyond that every warp parks so many tiles that
+// a full house would cost the second CTA per SM, so half the warps solve in twice the rounds
+__host__ __device__ constexpr int solver_warps(int NT) { return NT <= 7 ? NWARP : NWARP / 2; }
 __host__ __device__ constexpr int stage_count(int NT) {
     int need = NT * NT;                                                          // in 8x8 tiles
-    if (NWARP * lean_nsmt(NT) > need) need = NWARP * lean_nsmt(NT);
+    if (solver_warps(NT) * lean_nsmt(NT) > need) need = solver_warps(NT) * lean_nsmt(NT);
     if (NWARP * NT > need) need = NWARP * NT;
+    // partial Z tiles of the H-pass: Zfull + (NKG - 1) triangles, minus what J and the trial vectors behind the ring hold
+    const int hneed = NT * NT + (NKG - 2) * (NT * (NT + 1) / 2) - 2 * NT;
+    if (hneed > need) need = hneed;
     int nst = (need + CH * NT - 1) / (CH * NT);
     if (nst < 2) nst = 2;
     return nst + MX_NST_EXTRA;
@@ -208,7 +214,7 @@ struct Lay {
     static constexpr int total = o_bar + 2 * NST;
     static_assert(NT * NT * 64 <= NST * STAGE_D, "Zfull must fit in the staging area");
     static_assert(NWARP * 8 * SP <= NST * STAGE_D, "yred must fit in the staging area");
-    static_assert(NWARP * Lean<NT>::NSMT * 64 <= NST * STAGE_D, "the parked Cholesky tiles must fit in the staging area");
+    static_assert(solver_warps(NT) * Lean<NT>::NSMT * 64 <= NST * STAGE_D, "the parked tiles of the solver warps must fit in the staging area");
     static_assert(Lean<NT>::NSMT <= NTRI, "the parked tiles of the log-det factorisation must fit in the J area");
     static_assert(NT * NT * 64 + (NKG - 1) * NTRI * 64 <= o_ctb, "partial Z tiles of the H-pass must fit behind Zfull");
 };
@@ -920,10 +926,11 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
     // ---- P3: factorise J + shift(mu_u) and solve for every unique trial (one solver warp per matrix) -------
     auto solve_trials = [&]() {
         const int nuniq = ctl.nuniq;
-        // every warp factorises one shifted Hessian at a time (NWARP trials per round); the strictly-lower tiles of
-        // the leading block columns are parked in this warp's slice of the idle staging ring
+        // every solver warp factorises one shifted Hessian at a time; the strictly-lower tiles of the leading block
+        // columns are parked in this warp's slice of the idle staging ring
+        constexpr int NSOLVE = solver_warps(NT);
         double* const Lsm = sm + LY::o_stage + LY::NST * LY::STAGE_D - (warp + 1) * LN::NSMT * 64;
-        for (int u = warp; u < nuniq; u += NWARP) {
+        for (int u = warp; u < nuniq && warp < NSOLVE; u += NSOLVE) {
             const double mu = ctl.umu[u];
             auto load = [&](int I, int J) -> double2 {
                 double2 v = *reinterpret_cast<const double2*>(sm + LY::o_J + tri(I, J) * 64 + 2 * lane);

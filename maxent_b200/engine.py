@@ -176,21 +176,10 @@ class SharedProblem(object):
         if not hasattr(self, "svd_sweeps"):
             self.svd_sweeps = None
         if method == "jacobi":
-            m, n = K.shape
-            tr = m < n
-            Kk = K.transpose(0, 1).contiguous() if tr else K
-            m2, n2 = Kk.shape
-            U = torch.empty((m2, n2), dtype=torch.float64, device=K.device)
-            S = torch.empty((n2,), dtype=torch.float64, device=K.device)
-            V = torch.empty((n2, n2), dtype=torch.float64, device=K.device)
-            work = torch.empty((m2 * n2 + n2 * n2 + n2 + 8,), dtype=torch.float64, device=K.device)
-            sweeps = ctypes.c_int32(0)
-            stream = ctypes.c_void_p(torch.cuda.current_stream(K.device).cuda_stream)
-            _lib.check(self.lib.mx_svd_jacobi(_ptr(Kk), m2, n2, _ptr(U), _ptr(S), _ptr(V), _ptr(work), 60,
-                                              ctypes.byref(sweeps), stream), "mx_svd_jacobi")
+            U, S, V, info = device_svd(K)
             if self.svd_sweeps is None:
-                self.svd_sweeps = sweeps.value
-            return (V, S, U) if tr else (U, S, V)
+                self.svd_sweeps = info
+            return U, S, V
         elif method == "torch":
             U, S, Vh = torch.linalg.svd(K, full_matrices=False)
             return U.contiguous(), S.contiguous(), Vh.transpose(0, 1).contiguous()
@@ -232,27 +221,67 @@ def matmul_host(A, B, device=None):
                 @ torch.as_tensor(np.ascontiguousarray(B, dtype=np.float64), device=dev)).cpu().numpy()
 
 
-def svd_jacobi_host(K, device=None, max_sweeps=60):
-    """Thin SVD K = U diag(S) V^T by the device one-sided Jacobi (mx_svd_jacobi), replacing np.linalg.svd in
-    KernelSVD.svd (python/kernels.py:53-64).  numpy in, numpy (U[m,k], S[k], V[n,k]) out, k = min(m, n)."""
-    torch = _require_cuda()
+SVD_DIRECT_MAX = 160      # matrices with min(m, n) up to this get the full one-sided Jacobi (mx_svd_jacobi)
+SVD_FIRST_RANK = 128      # first guess of the number of leading triplets of a larger matrix (mx_svd_truncated)
+SVD_FLOOR = 1.e-15        # a returned singular value below SVD_FLOOR * S[0] is at the rounding floor of the matrix
+SVD_SEED = 0x6d6178656e74  # the random range finder is reproducible
+
+
+def device_svd(K):
+    """SVD of a device tensor K[m, n] for KernelSVD.svd (python/kernels.py:53-64): (U[m, k], S[k], V[n, k], info).
+
+    Small matrices (min(m, n) <= SVD_DIRECT_MAX): full one-sided Jacobi, k = min(m, n).  Larger ones: the leading
+    triplets only (mx_svd_truncated), with k doubled until at least eight of the returned singular values sit at the
+    rounding floor -- then K = U S V^T holds to eps * S[0] and nothing above the floor is missing; a matrix that is
+    not numerically rank deficient ends at k = min(m, n), i.e. with the full SVD.  ``info`` says which route ran."""
+    torch = _torch()
     lib = _lib.load()
+    dev = K.device
+    f64 = torch.float64
+    m, n = int(K.shape[0]), int(K.shape[1])
+    kmin = min(m, n)
+    stream = _stream(dev)
+
+    def full():
+        tr = m < n
+        Kk = K.transpose(0, 1).contiguous() if tr else K.contiguous()
+        m2, n2 = int(Kk.shape[0]), int(Kk.shape[1])
+        U = torch.empty((m2, n2), dtype=f64, device=dev)
+        S = torch.empty((n2,), dtype=f64, device=dev)
+        V = torch.empty((n2, n2), dtype=f64, device=dev)
+        work = torch.empty((m2 * n2 + n2 * n2 + n2 + 64,), dtype=f64, device=dev)
+        _lib.check(lib.mx_svd_jacobi(_ptr(Kk), m2, n2, _ptr(U), _ptr(S), _ptr(V), _ptr(work), 60, None, stream),
+                   "mx_svd_jacobi")
+        return ((V, S, U) if tr else (U, S, V)) + ("jacobi, all %d columns" % n2,)
+
+    if kmin <= SVD_DIRECT_MAX:
+        return full()
+    Kc = K.contiguous()
+    p = SVD_FIRST_RANK
+    while p < kmin:
+        U = torch.empty((m, p), dtype=f64, device=dev)
+        S = torch.empty((p,), dtype=f64, device=dev)
+        V = torch.empty((n, p), dtype=f64, device=dev)
+        nwork = int(lib.mx_svd_truncated_work_doubles(m, n, p))
+        work = torch.empty((nwork,), dtype=f64, device=dev)
+        _lib.check(lib.mx_svd_truncated(_ptr(Kc), m, n, p, _ptr(U), _ptr(S), _ptr(V), _ptr(work), SVD_SEED, stream),
+                   "mx_svd_truncated")
+        Sh = S.cpu()
+        if int((Sh > SVD_FLOOR * float(Sh[0])).sum()) <= p - 8:
+            return U, S, V, "truncated, %d leading triplets" % p
+        p *= 2
+    return full()
+
+
+def svd_jacobi_host(K, device=None):
+    """KernelSVD.svd on the device (python/kernels.py:53-64): numpy in, numpy (U[m, k], S[k], V[n, k]) out; see
+    ``device_svd`` for k."""
+    torch = _require_cuda()
     dev = torch.device("cuda" if device is None else device)
     with torch.cuda.device(dev):
         Kd = torch.as_tensor(np.ascontiguousarray(K, dtype=np.float64), device=dev)
-        m, n = Kd.shape
-        tr = m < n
-        Kk = Kd.transpose(0, 1).contiguous() if tr else Kd
-        m2, n2 = Kk.shape
-        U = torch.empty((m2, n2), dtype=torch.float64, device=dev)
-        S = torch.empty((n2,), dtype=torch.float64, device=dev)
-        V = torch.empty((n2, n2), dtype=torch.float64, device=dev)
-        work = torch.empty((m2 * n2 + n2 * n2 + n2 + 8,), dtype=torch.float64, device=dev)
-        sweeps = ctypes.c_int32(0)
-        _lib.check(lib.mx_svd_jacobi(_ptr(Kk), m2, n2, _ptr(U), _ptr(S), _ptr(V), _ptr(work), int(max_sweeps),
-                                     ctypes.byref(sweeps), _stream(dev)), "mx_svd_jacobi")
-        U, S, V = U.cpu().numpy(), S.cpu().numpy(), V.cpu().numpy()
-    return (V, S, U) if tr else (U, S, V)
+        U, S, V, _ = device_svd(Kd)
+        return U.cpu().numpy(), S.cpu().numpy(), V.cpu().numpy()
 
 
 class SweepResult(object):
