@@ -153,25 +153,7 @@ def main():
     np.savez_compressed(os.path.join(GOLD, "g5b_config1_default_cut.npz"), **out)
     print("g5b", out["ref_n_sv"], out["ref_wall"], out.get("ref_idx_LineFitAnalyzer"))
 
-    # --- G6: BASELINE config 2 = ElementwiseMaxEnt on the 2x2 fixture ----------------------------
-    #     (test/python/elementwise_maxent.py:110-117, use_hermiticity=True)
-    ew = m.ElementwiseMaxEnt(use_hermiticity=True)
-    ew.set_verbosity(m.VerbosityFlags.Quiet)
-    ew.set_G_tau_data(tau_e, G_e)
-    ew.omega = m.HyperbolicOmegaMesh(omega_min=-10, omega_max=10, n_points=80)
-    ew.alpha_mesh = m.LogAlphaMesh(alpha_min=0.05, alpha_max=500, n_points=8)
-    ew.set_error(1.e-3)
-    res = ew.run()
-    out = dict(tau=tau_e, G=G_e, err=1.e-3, omega=np.array(ew.omega), alpha_mesh=np.array(ew.alpha_mesh),
-               ref_alpha=np.array(res.alpha), ref_chi2=np.array(res.chi2), ref_S=np.array(res.S),
-               ref_A=np.array(res.A), ref_A_out=np.array(res.A_out))
-    for i in range(2):
-        for j in range(2):
-            ar = res.analyzer_results[i][j]
-            if ar:
-                out["ref_idx_LineFitAnalyzer_%d%d" % (i, j)] = int(ar["LineFitAnalyzer"]["alpha_index"])
-    np.savez_compressed(os.path.join(GOLD, "g6_elementwise_2x2.npz"), **out)
-    print("g6 done")
+    elementwise_cases(m)
     preblur_case(m)
     marquardt_case(m)
     mesh_case(m)
@@ -275,8 +257,100 @@ def covariance_case(m):
     print("g9", out["ref_n_sv"], out.get("ref_idx_LineFitAnalyzer"), out["noise_A"])
 
 
+def _matrix_run(m, cls, tau, G, scale=1.0, **kw):
+    """One elementwise-type run of the real reference on a matrix-valued G(tau) (test/python/elementwise_maxent.py:101-147)."""
+    ew = getattr(m, cls)(**kw)
+    ew.set_verbosity(m.VerbosityFlags.Quiet)
+    ew.set_G_tau_data(np.array(tau), np.array(G) * scale)
+    ew.omega = m.HyperbolicOmegaMesh(omega_min=-10, omega_max=10, n_points=80)
+    ew.alpha_mesh = m.LogAlphaMesh(alpha_min=0.05, alpha_max=500, n_points=8)
+    ew.set_error(1.e-3)
+    return ew, ew.run()
+
+
+def _matrix_fixture(m, cls, tau, G, **kw):
+    """Fixture of a matrix run + the reference's own reproducibility (re-run with G * (1 + 1e-15)), element by element."""
+    ew, res = _matrix_run(m, cls, tau, G, **kw)
+    _, res2 = _matrix_run(m, cls, tau, G, scale=1.0 + 1.e-15, **kw)
+    A1, A2 = np.array(res.A), np.array(res2.A)
+    c1, c2 = np.array(res.chi2), np.array(res2.chi2)
+    with np.errstate(all="ignore"):
+        nA = np.max(np.abs(A1 - A2), axis=-1) / np.max(np.abs(A1), axis=-1)
+        nc = np.abs(c2 / c1 - 1.0)
+    out = dict(tau=np.array(tau), G=np.array(G), err=1.e-3, omega=np.array(ew.omega), alpha_mesh=np.array(ew.alpha_mesh),
+               ref_alpha=np.array(res.alpha), ref_chi2=c1, ref_S=np.array(res.S), ref_A=A1, ref_A_out=np.array(res.A_out),
+               noise_A=nA, noise_chi2=nc, options=repr(sorted(kw.items())))
+    n = np.array(G).shape[0]
+    idx = np.full((n, n, 2), -1, dtype=np.int64)
+    for i in range(n):
+        for j in range(n):
+            ar = res.analyzer_results[i][j]
+            if isinstance(ar, (list, tuple)):                       # complex elements: [re, im]
+                for c, a in enumerate(ar):
+                    if a and "LineFitAnalyzer" in a:
+                        idx[i, j, c] = int(a["LineFitAnalyzer"]["alpha_index"])
+            elif ar and "LineFitAnalyzer" in ar:
+                idx[i, j, 0] = int(ar["LineFitAnalyzer"]["alpha_index"])
+    out["ref_idx_LineFitAnalyzer"] = idx
+    return out
+
+
+def elementwise_cases(m):
+    """G6 (BASELINE config 2 = ElementwiseMaxEnt on the reference's 2x2 fixture, now with the reference's own noise
+    floor), G10 (PoormanMaxEnt, python/elementwise_maxent.py:562-653) and G11 (complex matrix elements,
+    use_complex=True, python/elementwise_maxent.py:244-268, for both front ends): the front ends of
+    test/python/elementwise_maxent.py:101-147 and test/python/complex_elementwise_maxent.py:76-137."""
+    tests = os.path.join(REF, "test", "python")
+    with np.load(os.path.join(tests, "elementwise_g_tau.npz")) as data:
+        tau_e = data["tau"]
+        G_e = data["G_tau_noise"]
+    out = _matrix_fixture(m, "ElementwiseMaxEnt", tau_e, G_e, use_hermiticity=True)
+    for i in range(2):
+        for j in range(2):
+            if out["ref_idx_LineFitAnalyzer"][i, j, 0] >= 0:
+                out["ref_idx_LineFitAnalyzer_%d%d" % (i, j)] = int(out["ref_idx_LineFitAnalyzer"][i, j, 0])
+    np.savez_compressed(os.path.join(GOLD, "g6_elementwise_2x2.npz"), **out)
+    print("g6", out["noise_A"].max(), out["ref_idx_LineFitAnalyzer"][..., 0].tolist())
+    out = _matrix_fixture(m, "PoormanMaxEnt", tau_e, G_e, use_hermiticity=False)
+    np.savez_compressed(os.path.join(GOLD, "g10_poorman_2x2.npz"), **out)
+    print("g10", out["noise_A"].max(), out["ref_idx_LineFitAnalyzer"][..., 0].tolist())
+    # complex Hermitian matrix: the real fixture rotated by diag(1, exp(0.3 i))  (the reference's own complex test
+    # builds its data with TRIQS, test/python/complex_elementwise_maxent.py:41-87)
+    ph = np.exp(0.3j)
+    G_c = np.array(G_e, dtype=complex)
+    G_c[0, 1] = G_e[0, 1] * np.conjugate(ph)
+    G_c[1, 0] = G_e[1, 0] * ph
+    out = _matrix_fixture(m, "ElementwiseMaxEnt", tau_e, G_c, use_hermiticity=False, use_complex=True)
+    np.savez_compressed(os.path.join(GOLD, "g11_complex_elementwise_2x2.npz"), **out)
+    print("g11", out["ref_A"].shape, out["noise_A"].max(), out["ref_idx_LineFitAnalyzer"].tolist())
+    out = _matrix_fixture(m, "PoormanMaxEnt", tau_e, G_c, use_hermiticity=True, use_complex=True)
+    np.savez_compressed(os.path.join(GOLD, "g12_complex_poorman_2x2.npz"), **out)
+    print("g12", out["ref_A"].shape, out["noise_A"].max(), out["ref_idx_LineFitAnalyzer"].tolist())
+
+
+def config4_case(m):
+    """G13: BASELINE config 4 (n_tau = 10000, n_omega = 2000, 100 alphas, probability, cut 1e-11) -- one run of the real
+    reference (~10 min on 8 cores) plus its reproducibility run; A is stored at the analyzer picks and every tenth alpha."""
+    tau, G, om = synthetic(10000, 2000)
+    amesh = m.LogAlphaMesh(0.01, 2000, 100)
+    out, tm, res = run_reference(m, tau, G, 1.e-4, om, amesh, probability="normal", reduce_singular_space=1e-11,
+                                 noise_floor=True)
+    keep = sorted(set(list(range(0, 100, 10)) + [99] + [int(v) for k, v in out.items() if k.startswith("ref_idx_")]))
+    out["A_rows"] = np.array(keep)
+    out["ref_A"] = out["ref_A"][keep]
+    for k in ("ref_H", "ref_v", "tau", "omega", "G"):
+        out.pop(k)                                   # rebuilt from the recipe (seed 1234) in the test
+    out["G_sha_check"] = float(np.sum(G))
+    np.savez_compressed(os.path.join(GOLD, "g13_config4_10000x2000.npz"), **out)
+    print("g13", out["ref_n_sv"], out["ref_wall"], {k: v for k, v in out.items() if k.startswith("ref_idx_")})
+
+
 if __name__ == "__main__":
-    if "--covariance-only" in sys.argv:
+    if "--elementwise-only" in sys.argv:
+        elementwise_cases(import_reference())
+    elif "--config4-only" in sys.argv:
+        config4_case(import_reference())
+    elif "--covariance-only" in sys.argv:
         covariance_case(import_reference())
     elif "--meshes-only" in sys.argv:
         mesh_case(import_reference())

@@ -95,3 +95,36 @@ def check_against_reference(g, res, b=0, rtol_chi2_S=RTOL_WELL_DETERMINED):
         btol = max(1.e-6, float(np.sum(w * tolA) * 2))
         assert np.max(np.abs(Aout[4] - ref)) <= btol * np.max(np.abs(ref)), (np.max(np.abs(Aout[4] - ref)), btol)
     return dict(dA=dA, dchi2=dc)
+
+
+def check_matrix_result(res, g, hermitian_copy=()):
+    """The tiered contract (T2-T4) element by element for the matrix front ends (ElementwiseMaxEnt, PoormanMaxEnt, with
+    or without complex elements) against a run of the real reference: A and chi2 within 1e-8 where the reference
+    reproduces itself, 10x its own noise floor elsewhere; LineFit picks identical; A_out at the tolerance of the pick.
+    Elements the reference did not compute (NaN) must be NaN here too."""
+    refA, refc = g["ref_A"], g["ref_chi2"]
+    A, chi2 = np.asarray(res.A), np.asarray(res.chi2)
+    assert A.shape == refA.shape and chi2.shape == refc.shape, (A.shape, refA.shape)
+    worst = 0.0
+    for el in np.ndindex(*refc.shape[:-1]):
+        if np.all(np.isnan(refc[el])):
+            assert np.all(np.isnan(chi2[el])), el
+            continue
+        tolA = np.maximum(RTOL_WELL_DETERMINED, NOISE_FACTOR * running_max(np.nan_to_num(g["noise_A"][el])))
+        tolc = np.maximum(RTOL_WELL_DETERMINED, NOISE_FACTOR * running_max(np.nan_to_num(g["noise_chi2"][el])))
+        dA = rel_A(A[el], refA[el])
+        assert np.all(dA <= tolA), (el, dA / tolA)
+        dc = np.abs(chi2[el] / refc[el] - 1.0)
+        assert np.all(dc <= tolc), (el, dc / tolc)
+        worst = max(worst, float(np.max(dA / tolA)))
+        ij, c = el[:2], (el[2] if len(el) > 2 else 0)
+        k = int(g["ref_idx_LineFitAnalyzer"][ij[0], ij[1], c])
+        ar = res.analyzer_results[ij[0]][ij[1]]
+        ar = ar[c] if isinstance(ar, (list, tuple)) else ar
+        assert int(ar["LineFitAnalyzer"]["alpha_index"]) == k, (el, ar["LineFitAnalyzer"]["alpha_index"], k)
+        ref_out = refA[el][k]
+        assert np.max(np.abs(np.asarray(ar["LineFitAnalyzer"]["A_out"]) - ref_out)) <= tolA[k] * np.max(np.abs(ref_out)), el
+    ro, mo_ = g["ref_A_out"], np.asarray(res.A_out)
+    assert np.array_equal(np.isnan(ro), np.isnan(mo_))
+    assert np.nanmax(np.abs(mo_ - ro)) <= 1e-7 * np.nanmax(np.abs(ro))
+    return worst

@@ -178,15 +178,8 @@ def test_elementwise_matches_reference_run():
     np.testing.assert_allclose(res.alpha, g["ref_alpha"], rtol=1e-14)
     np.testing.assert_array_equal(res.A[1, 0], res.A[0, 1])           # hermiticity: exact copy
     assert np.all(np.isnan(res.chi2[1, 0]))                           # (1,0) was not computed
-    for (i, j) in ((0, 0), (0, 1), (1, 1)):
-        assert res.analyzer_results[i][j]['LineFitAnalyzer']['alpha_index'] == int(g["ref_idx_LineFitAnalyzer_%d%d" % (i, j)])
-        np.testing.assert_allclose(res.chi2[i, j], g["ref_chi2"][i, j], rtol=1e-6)
-        scale = np.max(np.abs(g["ref_A"][i, j]), axis=-1, keepdims=True)
-        k = res.analyzer_results[i][j]['LineFitAnalyzer']['alpha_index']
-        assert np.max(np.abs(res.A[i, j, k] - g["ref_A"][i, j, k])) <= 1e-8 * scale[k]
-        assert np.max(np.abs(res.A[i, j, :k + 1] - g["ref_A"][i, j, :k + 1]) / scale[:k + 1]) < 1e-6
-    ref_out = g["ref_A_out"]
-    assert np.nanmax(np.abs(res.A_out - ref_out)) <= 1e-8 * np.nanmax(np.abs(ref_out))
+    # BASELINE config 2 under the tiered contract: 1e-8 where the reference reproduces itself, 10x its noise elsewhere
+    gc.check_matrix_result(res, g)
     # diagonal-only run gives the same diagonal elements (bitwise: same kernel, same launch shape per element)
     dg = make(mb.DiagonalMaxEnt)
     rd = dg.run()
@@ -203,6 +196,43 @@ def test_elementwise_matches_reference_run():
     for i in range(2):
         assert abs(np.trapezoid(res.A_out[i, i], om) - 1.0) < 1e-2
     assert abs(np.trapezoid(res.A_out[0, 1], om)) < 1e-2
+
+
+def _matrix_front_end(cls, g, **kw):
+    ew = cls(**kw)
+    ew.set_verbosity(mb.VerbosityFlags.Quiet)
+    ew.set_G_tau_data(g["tau"], g["G"])
+    ew.omega = mb.DataOmegaMesh(g["omega"])
+    ew.alpha_mesh = mb.DataAlphaMesh(g["alpha_mesh"])
+    ew.set_error(float(g["err"]))
+    return ew
+
+
+def test_poorman_matches_reference_run():
+    """PoormanMaxEnt (python/elementwise_maxent.py:562-653; test/python/elementwise_maxent.py:131-147) against the run
+    of the real reference on its own 2x2 fixture (g10): every element under the tiered contract."""
+    g = gc.load_golden("g10_poorman_2x2.npz")
+    res = _matrix_front_end(mb.PoormanMaxEnt, g, use_hermiticity=False).run()
+    gc.check_matrix_result(res, g)
+    herm = _matrix_front_end(mb.PoormanMaxEnt, g, use_hermiticity=True).run()
+    np.testing.assert_array_equal(herm.A_out[0, 1], herm.A_out[1, 0])            # test/python/elementwise_maxent.py:151-152
+    np.testing.assert_allclose(herm.A[0, 1], res.A[0, 1], rtol=0, atol=1e-9 * np.max(np.abs(res.A[0, 1])))
+
+
+def test_complex_elements_match_reference_runs():
+    """use_complex=True (python/elementwise_maxent.py:244-268, 633-652; test/python/complex_elementwise_maxent.py:76-137)
+    for ElementwiseMaxEnt and PoormanMaxEnt against runs of the real reference on a complex Hermitian G(tau) (g11, g12):
+    real and imaginary parts of every element under the tiered contract, same NaN pattern, Hermitian A_out."""
+    g = gc.load_golden("g11_complex_elementwise_2x2.npz")
+    res = _matrix_front_end(mb.ElementwiseMaxEnt, g, use_hermiticity=False, use_complex=True).run()
+    assert res.A.shape == (2, 2, 2, 8, 80)
+    gc.check_matrix_result(res, g)
+    g = gc.load_golden("g12_complex_poorman_2x2.npz")
+    res = _matrix_front_end(mb.PoormanMaxEnt, g, use_hermiticity=True, use_complex=True).run()
+    gc.check_matrix_result(res, g)
+    A_out = res.A_out
+    for iw in range(A_out.shape[-1]):                                             # complex_elementwise_maxent.py:139-143
+        assert np.all(A_out[..., iw] == A_out[..., iw].conjugate().transpose())
 
 
 def test_poorman_runs_and_uses_diagonal_default_model():
