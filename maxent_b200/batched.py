@@ -47,7 +47,10 @@ def synthetic_bootstrap_batch(n_tau, n_omega, n_spectra, first=0, seed=5, beta=4
     with np.errstate(over="ignore"):
         K = np.where(ww >= 0, -np.exp(-ww * tt) / (np.exp(-beta * ww) + 1.0),
                      -np.exp(np.minimum(ww, 0) * (beta - tt)) / (1.0 + np.exp(beta * np.minimum(ww, 0))))
-    G_exact = (K * omega.delta[None, :]) @ A
+    # fixed summation order: numpy's (single-threaded, pairwise) reduction instead of a BLAS GEMV whose blocking -- and
+    # therefore the last bits of G -- depends on the thread count of the host (torchrun sets OMP_NUM_THREADS=1, a plain
+    # run does not: round 1 saw 887.88 vs 887.80 LM iterations per spectrum for "the same" batch)
+    G_exact = (K * (omega.delta * A)[None, :]).sum(axis=1)
     rng = np.random.default_rng(seed)
     if first:
         # rows [0, first) belong to lower ranks: skip them in blocks instead of materialising them

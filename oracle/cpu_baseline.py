@@ -48,9 +48,31 @@ def bench_inputs(n_tau, n_omega, n_spectra, seed=5, first=0):
 
 
 def _init(n_tau, n_omega, n_alpha, n_spectra, thr, seed):
-    _P["pr"] = bench_inputs(n_tau, n_omega, n_spectra, seed)
+    _P["pr"] = bench_inputs(n_tau, n_omega, n_spectra, seed, first=_P.get("first", 0))
     _P["mesh"] = mo.log_alpha_mesh(0.01, 2000, n_alpha)
     _P["thr"] = thr
+
+
+def _perturbed(task):
+    """One rounding-level perturbation of the oracle run of spectrum b (SURVEY.md 8(c) tier T4: the oracle's own
+    reproducibility): v = 1, 2: G * (1 +- 1e-15); v = 3: the other LAPACK SVD driver (gesvd instead of numpy's gesdd --
+    the singular vectors next to the cut are only determined to ~eps * S[0] / S[k])."""
+    b, v = task
+    pr = _P["pr"]
+    G = pr["G"][b]
+    svd = None
+    if v == 1:
+        G = G * (1.0 + 1.e-15)
+    elif v == 2:
+        G = G * (1.0 - 1.e-15)
+    else:
+        import scipy.linalg
+        U, S, Vh = scipy.linalg.svd(pr["K"], full_matrices=False, lapack_driver="gesvd")
+        keep = S >= _P["thr"]
+        svd = (U[:, keep], S[keep], Vh.T[:, keep])
+    o2 = mo.maxent_loop(pr["K"], G, pr["err"], pr["omega"], _P["mesh"], reduce_singular_space=_P["thr"], fast_d2=True,
+                        analyzers=False, svd=svd)
+    return dict(b=b, v=v, A=o2["A"], chi2=o2["chi2"])
 
 
 def _one(b):
@@ -68,11 +90,12 @@ def _one(b):
                 linefit=int(an["LineFitAnalyzer"]["alpha_index"]), chi2curv=int(an["Chi2CurvatureAnalyzer"]["alpha_index"]))
 
 
-def run(n_tau, n_omega, n_alpha, spectra, procs, thr=1e-11, seed=5, dump=None, kpoints=0, krows=None):
+def run(n_tau, n_omega, n_alpha, spectra, procs, thr=1e-11, seed=5, dump=None, kpoints=0, krows=None, first=0, noise=False):
     import multiprocessing as mp
     ctx = mp.get_context("fork")
     t0 = time.perf_counter()
     _P["keep"] = dump is not None            # inherited by the forked workers
+    _P["first"], _P["noise"] = first, bool(noise)
     _P["kpoints"], _P["krows"] = kpoints, (None if not kpoints else list(krows))
     if kpoints:
         spectra = len(krows)
@@ -81,11 +104,23 @@ def run(n_tau, n_omega, n_alpha, spectra, procs, thr=1e-11, seed=5, dump=None, k
         rows = [_one(b) for b in range(spectra)]
     else:
         with ctx.Pool(procs, initializer=_init, initargs=(n_tau, n_omega, n_alpha, spectra, thr, seed)) as pool:
+            pert = pool.map_async(_perturbed, [(b, v) for v in (1, 2, 3) for b in range(spectra)], chunksize=1) if noise else None
             rows = pool.map(_one, range(spectra), chunksize=1)
+            pert = pert.get() if pert is not None else []
+        for r in pert:                       # noise floor = largest movement over the three perturbations
+            a = rows[r["b"]]["arrays"]
+            nA = np.max(np.abs(r["A"] - a["A"]), axis=1) / np.max(np.abs(a["A"]), axis=1)
+            nc = np.abs(r["chi2"] / a["chi2"] - 1.0)
+            a["noise_A"] = np.maximum(a.get("noise_A", 0.0), nA)
+            a["noise_chi2"] = np.maximum(a.get("noise_chi2", 0.0), nc)
     wall = time.perf_counter() - t0
     if dump is not None:                     # the oracle's own outputs, for the full-size parity test
-        pr = bench_inputs(n_tau, n_omega, spectra, seed)
-        np.savez(dump, G=pr["G"], A=np.stack([r["arrays"]["A"] for r in rows]), chi2=np.stack([r["arrays"]["chi2"] for r in rows]),
+        pr = bench_inputs(n_tau, n_omega, spectra, seed, first=first)
+        extra = {}
+        if noise:
+            extra = dict(noise_A=np.stack([r["arrays"]["noise_A"] for r in rows]),
+                         noise_chi2=np.stack([r["arrays"]["noise_chi2"] for r in rows]))
+        np.savez(dump, G=pr["G"], **extra, A=np.stack([r["arrays"]["A"] for r in rows]), chi2=np.stack([r["arrays"]["chi2"] for r in rows]),
                  S=np.stack([r["arrays"]["S"] for r in rows]), Q=np.stack([r["arrays"]["Q"] for r in rows]),
                  n_iter=np.stack([r["arrays"]["n_iter"] for r in rows]), linefit=np.array([r["linefit"] for r in rows]),
                  chi2curv=np.array([r["chi2curv"] for r in rows]))
@@ -108,12 +143,15 @@ def main():
     ap.add_argument("--dump", default=None, help="write the oracle's A/chi2/S/Q/picks of the sample to this .npz")
     ap.add_argument("--kpoints", type=int, default=0, help="k-resolved recipe (C3): size of the k mesh")
     ap.add_argument("--krows", default="", help="comma-separated k values to run (with --kpoints)")
+    ap.add_argument("--first", type=int, default=0, help="first row of the benchmark batch to run (rows of another rank's shard)")
+    ap.add_argument("--noise-floor", action="store_true",
+                    help="with --dump and --procs > 1: also run three rounding-level perturbations of every spectrum")
     a = ap.parse_args()
     procs = a.procs or (os.cpu_count() or 1)
     spectra = a.spectra or procs
     krows = [int(x) for x in a.krows.split(",") if x]
     print(json.dumps(run(a.n_tau, a.n_omega, a.n_alpha, spectra, procs, a.thr, dump=a.dump, kpoints=a.kpoints,
-                         krows=krows)))
+                         krows=krows, first=a.first, noise=a.noise_floor)))
 
 
 if __name__ == "__main__":

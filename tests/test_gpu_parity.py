@@ -437,21 +437,18 @@ def test_all_kernel_instantiations_vs_oracle(torch_cuda, n_sv_target):
     assert bool((res.status & 1).all())
 
 
-def test_full_size_sample_vs_oracle(torch_cuda, tmp_path):
-    """BASELINE config 3/5 shape (n_tau = 2000, n_omega = 1000, 60 alphas, cut 1e-11): the first four spectra of the
-    benchmark batch against the oracle run on the host cores (one process per spectrum, ~30 s).  Tolerances follow the
-    reference's own reproducibility at this shape (A_alpha reproducible to <= 2e-11 up to alpha
-    index 36, 4e-9 ... 4e-5 in the small-alpha tail): identical LineFit / Chi2Curvature picks, A and chi2 within 1e-8
-    for alpha index <= 36, the tail within 1e-3 (A) / 1e-6 (chi2)."""
+def _full_size_vs_oracle(tmp_path, first, n, extra=()):
     import os, subprocess, sys
-    from maxent_b200 import engine
+    from maxent_b200 import engine, batched
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    dump = str(tmp_path / "oracle_full.npz")
-    n = 4
+    dump = str(tmp_path / ("oracle_full_%d.npz" % first))
     subprocess.run([sys.executable, "-m", "oracle.cpu_baseline", "--n-tau", "2000", "--n-omega", "1000", "--n-alpha", "60",
-                    "--spectra", str(n), "--procs", str(n), "--thr", "1e-11", "--dump", dump], cwd=root, check=True,
-                   capture_output=True)
+                    "--spectra", str(n), "--procs", str(4 * n), "--thr", "1e-11", "--dump", dump, "--noise-floor",
+                    "--first", str(first)] + list(extra), cwd=root, check=True, capture_output=True)
     o = np.load(dump)
+    # the rows the benchmark itself feeds rank `first // 8192` (same generator, same offset)
+    Gb = batched.synthetic_bootstrap_batch(2000, 1000, n, first=first, seed=5).numpy()
+    np.testing.assert_allclose(Gb, o["G"], rtol=0, atol=1e-14)
     pr = mo.synthetic_problem(2000, 1000, mu=np.ones(1), noise=np.zeros((1, 2000)))
     D = mo.flat_default_model(pr["omega"])
     prob = engine.SharedProblem(pr["K"], pr["err"], D, pr["delta"], reduce_singular_space=1e-11)
@@ -459,15 +456,55 @@ def test_full_size_sample_vs_oracle(torch_cuda, tmp_path):
     res = engine.run_sweep(prob, o["G"], alpha)
     A = res.A.cpu().numpy()
     idx = res.alpha_index.cpu().numpy()
+    worst = 0.0
     for b in range(n):
         assert idx[b, 0] == o["linefit"][b] and idx[b, 1] == o["chi2curv"][b], (b, idx[b, :2], o["linefit"][b], o["chi2curv"][b])
+        # tiered contract with the MEASURED floor of this spectrum: 1e-8 where the oracle reproduces itself under a 1e-15
+        # perturbation of G, 10x its own noise (running max over +-2 alphas) in the small-alpha tail
+        tolA = np.maximum(1e-8, 10 * gc.running_max(o["noise_A"][b]))
+        tolc = np.maximum(1e-8, 10 * gc.running_max(o["noise_chi2"][b]))
         dA = gc.rel_A(A[b], o["A"][b])
-        assert np.all(dA[:37] <= 1e-8), (b, dA[:37].max(), int(dA[:37].argmax()))
-        assert np.all(dA <= 1e-3), (b, dA.max())
+        assert np.all(dA <= tolA), (b, (dA / tolA).max(), int((dA / tolA).argmax()))
         dc = np.abs(res.chi2[b].cpu().numpy() / o["chi2"][b] - 1)
-        assert np.all(dc[:37] <= 1e-8) and np.all(dc <= 1e-6), (b, dc.max())
+        assert np.all(dc <= tolc), (b, (dc / tolc).max(), int((dc / tolc).argmax()))
+        assert np.all(tolA[:35] == 1e-8), tolA[:37]          # the well-determined range really is held to 1e-8
         for k in (idx[b, 0], idx[b, 1]):
             assert dA[k] <= 1e-8
+        worst = max(worst, float((dA / tolA).max()))
+    return worst
+
+
+def test_full_size_sample_vs_oracle(torch_cuda, tmp_path):
+    """BASELINE config 3/5 shape (n_tau = 2000, n_omega = 1000, 60 alphas, cut 1e-11): the first four spectra of the
+    benchmark batch against the oracle run on the host cores (four oracle runs per spectrum: three rounding-level
+    perturbations -- G * (1 +- 1e-15), the other LAPACK SVD driver -- measure the oracle's own noise floor per alpha).  Identical LineFit / Chi2Curvature picks; A and chi2
+    within 1e-8 wherever the oracle reproduces itself, within 10x its measured floor in the small-alpha tail."""
+    _full_size_vs_oracle(tmp_path, 0, 4)
+
+
+def test_full_size_rows_of_another_ranks_shard_vs_oracle(torch_cuda, tmp_path):
+    """The same comparison on rows 8192+37 ... of the 65,536-spectrum batch, i.e. spectra that rank 1 of the 8-GPU job
+    owns (bench.py shards 8192 per GPU and skips the generator ahead, batched.synthetic_bootstrap_batch(first=...))."""
+    _full_size_vs_oracle(tmp_path, 8192 + 37, 3)
+
+
+def test_full_size_run_to_run_determinism(torch_cuda):
+    """Two launches of the benchmark-shape sweep on the same 592 spectra (two per CTA slot, dynamic work distribution):
+    every output bit for bit the same -- spectra do not interact and every reduction inside a spectrum has a fixed order."""
+    torch = torch_cuda
+    from maxent_b200 import engine, batched
+    pr = mo.synthetic_problem(2000, 1000, mu=np.ones(1), noise=np.zeros((1, 2000)))
+    prob = engine.SharedProblem(pr["K"], pr["err"], mo.flat_default_model(pr["omega"]), pr["delta"], reduce_singular_space=1e-11)
+    G = batched.synthetic_bootstrap_batch(2000, 1000, 592, seed=5).cuda()
+    alpha = mo.log_alpha_mesh(0.01, 2000, 60) * 2000
+    r1 = engine.run_sweep(prob, G, alpha)
+    r2 = engine.run_sweep(prob, G.flip(0).contiguous(), alpha)          # other order: other CTAs, other co-residents
+    for f in ("A", "chi2", "S", "Q", "v", "alpha_index", "n_iter", "n_solve"):
+        assert torch.equal(getattr(r1, f), getattr(r2, f).flip(0)), f
+    # a second problem object built from scratch (kernel SVD included) gives the same bits as well
+    prob2 = engine.SharedProblem(pr["K"], pr["err"], mo.flat_default_model(pr["omega"]), pr["delta"], reduce_singular_space=1e-11)
+    r3 = engine.run_sweep(prob2, G[:64], alpha)
+    assert torch.equal(r1.A[:64], r3.A) and torch.equal(r1.chi2[:64], r3.chi2)
 
 
 def test_config3_k_resolved_batch_vs_oracle(torch_cuda, tmp_path):
@@ -475,8 +512,8 @@ def test_config3_k_resolved_batch_vs_oracle(torch_cuda, tmp_path):
     n_tau = 2000, n_omega = 1000, 60 alphas, LineFit + Chi2Curvature.  The whole batch runs in one launch; the k points
     0 / 700 / 1024 / 2048 (mu = 2, 0.95, 0, -2; oracle picks 25/22/21/25 and 31/28/27/31) are compared with the oracle
     run on the host cores.  Tolerances follow the oracle's own reproducibility on these four spectra under a 1e-15
-    perturbation of G (<= 1e-9 up to alpha index 34, 5e-6 ... 1e-4 in the small-alpha tail): identical picks, A and
-    chi2 within 1e-8 for alpha index <= 33 and at the picks, the tail within 1e-3 (A) / 1e-6 (chi2).  Batch-wide,
+    perturbation of G, measured in the same run: identical picks, A and chi2 within 1e-8 wherever the oracle reproduces
+    itself (alpha index <= 31 at least), within 10x its measured floor in the small-alpha tail.  Batch-wide,
     size-independent properties: every alpha converged, the picked spectra are positive, normalised, and peak at mu_k."""
     import os, subprocess, sys
     from maxent_b200 import engine
@@ -484,8 +521,8 @@ def test_config3_k_resolved_batch_vs_oracle(torch_cuda, tmp_path):
     dump = str(tmp_path / "oracle_c3.npz")
     rows = [0, 700, 1024, 2048]
     subprocess.run([sys.executable, "-m", "oracle.cpu_baseline", "--n-tau", "2000", "--n-omega", "1000", "--n-alpha", "60",
-                    "--kpoints", "4096", "--krows", ",".join(map(str, rows)), "--procs", str(len(rows)), "--thr", "1e-11",
-                    "--dump", dump], cwd=root, check=True, capture_output=True)
+                    "--kpoints", "4096", "--krows", ",".join(map(str, rows)), "--procs", str(4 * len(rows)), "--thr", "1e-11",
+                    "--dump", dump, "--noise-floor"], cwd=root, check=True, capture_output=True)
     o = np.load(dump)
     nk = 4096
     mu = 2.0 * np.cos(2.0 * np.pi * np.arange(nk) / nk)
@@ -499,11 +536,13 @@ def test_config3_k_resolved_batch_vs_oracle(torch_cuda, tmp_path):
     idx = res.alpha_index.cpu().numpy()
     for j, b in enumerate(rows):
         assert idx[b, 0] == o["linefit"][j] and idx[b, 1] == o["chi2curv"][j], (b, idx[b, :2], o["linefit"][j], o["chi2curv"][j])
+        tolA = np.maximum(1e-8, 10 * gc.running_max(o["noise_A"][j]))
+        tolc = np.maximum(1e-8, 10 * gc.running_max(o["noise_chi2"][j]))
         dA = gc.rel_A(res.A[b].cpu().numpy(), o["A"][j])
-        assert np.all(dA[:34] <= 1e-8), (b, dA[:34].max(), int(dA[:34].argmax()))
-        assert np.all(dA <= 1e-3), (b, dA.max())
+        assert np.all(dA <= tolA), (b, (dA / tolA).max(), int((dA / tolA).argmax()))
         dc = np.abs(res.chi2[b].cpu().numpy() / o["chi2"][j] - 1)
-        assert np.all(dc[:34] <= 1e-8) and np.all(dc <= 1e-6), (b, dc.max())
+        assert np.all(dc <= tolc), (b, (dc / tolc).max(), int((dc / tolc).argmax()))
+        assert np.all(tolA[:32] == 1e-8)
     # the whole batch
     assert bool((res.status & 1).all())
     assert idx[:, 0].min() >= 15 and idx[:, 0].max() <= 32 and idx[:, 1].min() >= 20 and idx[:, 1].max() <= 38
