@@ -32,6 +32,12 @@ extern "C" {
 #define MX_ENGINE_LOCKSTEP   1   /* retired (round-1 lock-step engine): requesting it returns MX_ERR_UNSUPPORTED */
 #define MX_ENGINE_SPECTRUM_CTA 2 /* one spectrum per CTA, speculative damping batches (csrc/mx_sweep2.cuh)    */
 
+/* MxProblem.per_spectrum_model bits */
+#define MX_PER_SPECTRUM_MODEL 1
+#define MX_PER_SPECTRUM_XI    2
+#define MX_PER_SPECTRUM_VT    4
+#define MX_PER_SPECTRUM_ALPHA 8
+
 /* cost-function variants (python/maxent_loop.py:106-121) */
 #define MX_VARIANT_NORMAL    0   /* MaxEntCostFunction + NormalEntropy + NormalH_of_v   */
 #define MX_VARIANT_PLUSMINUS 1   /* MaxEntCostFunction + PlusMinusEntropy + PlusMinusH_of_v */
@@ -47,7 +53,8 @@ extern "C" {
 
 /* per-(spectrum, alpha) status bits */
 #define MX_STATUS_CONVERGED  1   /* LevenbergMinimizer.converged (levenberg_minimizer.py:162-174) */
-#define MX_STATUS_SKIPPED    2   /* max|G| < G_threshold (maxent_loop.py:174-179) */
+#define MX_STATUS_SKIPPED    2   /* max|G| < G_threshold (maxent_loop.py:174-179): set by the host front end, which
+                                  * leaves such spectra out of the launch (maxent_b200/batched.py) */
 
 /* Levenberg-Marquardt parameters = LevenbergMinimizer.__init__ (levenberg_minimizer.py:92-121)
  * with the default convergence MaxDerivative(1e-4) | RelativeFunctionChange(1e-16); a criterion is switched off
@@ -75,9 +82,17 @@ typedef struct {
     int32_t variant;          /* MX_VARIANT_*                                                */
     int32_t want_probability; /* NormalLogProbability (probabilities.py:76-85)               */
     int32_t engine;           /* MX_ENGINE_*                                                 */
-    int32_t per_spectrum_model; /* 0: D[n_omega], v0[n_sv] shared by the batch; 1: D[B, ldD], v0[B, n_sv] with the row
-                               * stride ldD = n_omega rounded up to an even number (16-byte aligned rows)
-                               * (PoormanMaxEnt off-diagonals, python/elementwise_maxent.py:633-652)         */
+    int32_t per_spectrum_model; /* bit mask.  MX_PER_SPECTRUM_MODEL: D[B, ldD], v0[B, n_sv] instead of D[n_omega], v0[n_sv],
+                               * row stride ldD = n_omega rounded up to an even number (16-byte aligned rows)
+                               * (PoormanMaxEnt off-diagonals, python/elementwise_maxent.py:633-652).
+                               * MX_PER_SPECTRUM_XI: xi[B, n_sv] instead of xi[n_sv] -- every spectrum carries its own
+                               * scalar error bar, Xi_b = S / sigma_b (TauMaxEnt.set_error per data set,
+                               * python/tau_maxent.py:227-251); G is then passed already divided by sigma_b.
+                               * MX_PER_SPECTRUM_VT: spectra belong to groups with different error vectors / covariances,
+                               * i.e. different whitening rotations: see vt_index (xi, D, v0 per spectrum as well).
+                               * MX_PER_SPECTRUM_ALPHA: alpha[B, n_alpha] -- scale_alpha = 'Ndata' multiplies alpha by the
+                               * number of data rows (python/maxent_loop.py:216-220), which differs between groups whose
+                               * covariance matrices drop different numbers of eigenvalues */
     double  chi2_factor;      /* MaxEntCostFunction chi2_factor (cost_function.py:43-53)     */
     const double* Vt;         /* swizzled tile-major V' written by mx_layout_V               */
     const double* Qw;         /* [n_tau, n_sv]  sqrt(W) Q : g~ = Qw^T G                      */
@@ -89,6 +104,10 @@ typedef struct {
     const double* alpha;      /* [n_alpha]      alpha * scale_alpha, descending              */
     const double* v0;         /* [n_sv] or [B, n_sv]  initial v' (maxent_loop.py:196-203)    */
     MxLMParams lm;
+    const int32_t* vt_index;  /* MX_PER_SPECTRUM_VT: [B] index of the spectrum's whitening group; its V' starts at
+                               * Vt + vt_index[b] * vt_stride (every group: its own rotation V' = V_s P_g, python/tau_maxent.py:
+                               * 227-288 per data set); NULL otherwise */
+    int64_t vt_stride;        /* doubles between the V' buffers of consecutive groups (>= mx_layout_V_size) */
 } MxProblem;
 
 /* Outputs of the alpha sweep; any pointer may be NULL to skip that output (chi2/S/Q required). */

@@ -17,6 +17,8 @@ VARIANTS = {"normal": 0, "plusminus": 1, "bryan": 2}
 AN_LINEFIT, AN_CHI2CURV, AN_ENTROPY, AN_CLASSIC, AN_BRYAN = range(5)
 N_ANALYZERS = 5
 STATUS_CONVERGED = 1
+STATUS_SKIPPED = 2
+PER_SPECTRUM_MODEL, PER_SPECTRUM_XI, PER_SPECTRUM_VT, PER_SPECTRUM_ALPHA = 1, 2, 4, 8
 _ERR = {-1: "bad argument", -2: "unsupported (n_sv too large for the fused path?)", -3: "CUDA error",
         -4: "no CUDA device"}
 
@@ -39,7 +41,8 @@ class MxProblem(ctypes.Structure):
                 ("n_alpha", ctypes.c_int32), ("variant", ctypes.c_int32), ("want_probability", ctypes.c_int32),
                 ("engine", ctypes.c_int32), ("per_spectrum_model", ctypes.c_int32), ("chi2_factor", ctypes.c_double),
                 ("Vt", c_dp), ("Qw", c_dp), ("Qo", c_dp), ("sqrtw", c_dp), ("xi", c_dp), ("D", c_dp),
-                ("delta", c_dp), ("alpha", c_dp), ("v0", c_dp), ("lm", MxLMParams)]
+                ("delta", c_dp), ("alpha", c_dp), ("v0", c_dp), ("lm", MxLMParams), ("vt_index", c_dp),
+                ("vt_stride", ctypes.c_int64)]
 
 
 class MxSweepOut(ctypes.Structure):

@@ -166,16 +166,75 @@ class BatchedTauMaxEnt(object):
             self.set_kernel_tau(tau, None, None)
         self.G = G
 
-    def set_error(self, err):
-        """Scalar or [n_tau] vector shared by the batch (python/tau_maxent.py:227-251)."""
+    def set_error(self, err, per_spectrum=None):
+        """Error bars of the data (python/tau_maxent.py:227-251), for the batch:
+
+        * a scalar, or a vector [n_tau] -- shared by every spectrum;
+        * a vector [B] (``per_spectrum=True`` if B == n_tau) -- one scalar error bar per spectrum (bootstrap / QMC
+          batches): same singular space, Xi_b = S / sigma_b, still one launch;
+        * an array [B, n_tau] -- one error vector per spectrum: spectra with identical vectors form a group with its own
+          whitening rotation V' = V_s P_g; all groups run in ONE launch of the sweep (MxProblem.vt_index)."""
         self.err = err
+        self.cov = None
+        self._per_spectrum = per_spectrum
         self.problem = None
+        self._group_cache = {}
+
+    def set_cov(self, cov, cov_threshold=1.e-14):
+        """Covariance matrix of the data, [n_tau, n_tau] shared by the batch or [B, n_tau, n_tau] per spectrum
+        (TauMaxEnt.set_cov, python/tau_maxent.py:253-288): rotate into the eigenbasis, errors = sqrt(eigenvalues),
+        eigenvalues below ``cov_threshold`` dropped.  Identical matrices share one whitening group."""
+        cov = np.asarray(cov, dtype=np.float64)
+        assert np.max(np.abs(cov - np.swapaxes(cov, -1, -2))) < 1.e-10, 'Supplied covariance matrix is not symmetric.'
+        self.cov = cov
+        self.cov_threshold = cov_threshold
+        self.err = None
+        self.problem = None
+        self._group_cache = {}
+
+    def _error_plan(self, B):
+        """-> ('shared', None) | ('sigma', sigma[B]) | ('groups', index[B], [spec_g]) with spec = (T or None, err vector)."""
+        n_tau = len(self.tau) if self.tau is not None else self.K.shape[0]
+        if getattr(self, "cov", None) is not None:
+            covs = self.cov if self.cov.ndim == 3 else self.cov[None]
+            if self.cov.ndim == 3 and covs.shape[0] != B:
+                raise Exception("%d covariance matrices for %d spectra" % (covs.shape[0], B))
+            keys, specs, index = {}, [], np.zeros(B, dtype=np.int64)
+            for b in range(covs.shape[0]):
+                k = hash(covs[b].tobytes())
+                if k not in keys:
+                    e, v = np.linalg.eigh(covs[b])
+                    keep = e >= self.cov_threshold
+                    keys[k] = len(specs)
+                    specs.append((np.ascontiguousarray(v[:, keep].conjugate().T), np.sqrt(e[keep])))
+                index[b] = keys[k]
+            if self.cov.ndim == 2:
+                index[:] = 0
+            return "groups", index, specs
+        if self.err is None:
+            raise Exception("no error set: call set_error")
+        err = np.asarray(self.err, dtype=np.float64)
+        if err.ndim == 0 or (err.ndim == 1 and err.shape[0] == n_tau and not self._per_spectrum):
+            return "shared", None, None
+        if err.ndim == 1:
+            if err.shape[0] != B:
+                raise Exception("Supply a scalar error, one per tau point, one per spectrum, or an array [B, n_tau].")
+            return "sigma", err, None
+        if err.shape != (B, n_tau):
+            raise Exception("error array has shape %s, data has %s" % (err.shape, (B, n_tau)))
+        uniq, index = np.unique(err, axis=0, return_inverse=True)
+        return "groups", np.asarray(index).reshape(-1), [(None, u) for u in uniq]
 
     # ---- run --------------------------------------------------------------------------------------
     def prepare(self):
-        """Everything that depends on the kernel only (KernelSVD, truncation, layout); cached."""
-        if self.problem is not None:
+        """Everything that depends on the kernel only (KernelSVD, truncation, layout); cached, and rebuilt when one of the
+        public attributes it depends on was replaced (D, A_init, omega, reduce_singular_space, cost_function, svd)."""
+        key = (self.cost_function, None if self.reduce_singular_space is None else float(self.reduce_singular_space), self.svd,
+               id(self.omega), id(self.D), id(self.A_init), id(self.K), id(self.tau), self.beta)
+        if self.problem is not None and getattr(self, "_problem_key", None) == key:
             return self.problem
+        self._problem_key = key
+        self._group_cache = {}
         import torch
         if not torch.cuda.is_available():
             raise _lib.MaxEntLibraryError("maxent_b200 needs a CUDA device (no CPU fallback)")
@@ -194,13 +253,34 @@ class BatchedTauMaxEnt(object):
                                              K.data_ptr(), stream), "mx_tau_kernel")
             else:
                 K = torch.as_tensor(self.K, device=dev)
-        if self.err is None:
+        if self.err is None and getattr(self, "cov", None) is None:
             raise Exception("no error set: call set_error")
         D = FlatDefaultModel(omega).D if self.D is None else (self.D.D if hasattr(self.D, "D") else np.asarray(self.D))
-        self.problem = engine.SharedProblem(K, self.err, D, omega.delta, variant=self.cost_function,
-                                            reduce_singular_space=self.reduce_singular_space, device=dev,
-                                            svd=self.svd, A_init=self.A_init)
+        err = np.asarray(1.0 if self.err is None else self.err, dtype=np.float64)
+        shared = err.ndim == 0 or (err.ndim == 1 and err.shape[0] == K.shape[0] and not getattr(self, "_per_spectrum", None))
+        # per-spectrum error models: the base problem carries err = 1 (kernel SVD, truncation, V layout); error scales
+        # or whitening groups are attached per launch (run_device)
+        self._K_dev, self._D_host = K, D
+        self.problem = engine.SharedProblem(K, err if (shared and self.err is not None) else 1.0, D, omega.delta,
+                                            variant=self.cost_function, reduce_singular_space=self.reduce_singular_space,
+                                            device=dev, svd=self.svd, A_init=self.A_init)
         return self.problem
+
+    def _group_problem(self, g, spec):
+        """SharedProblem of one whitening group: the base kernel SVD with the group's error vector / covariance rotation."""
+        import torch
+        cache = self.__dict__.setdefault("_group_cache", {})
+        if g in cache:
+            return cache[g]
+        base = self.prepare()
+        T, err = spec
+        K, U = self._K_dev, base.U
+        if T is not None:
+            Td = torch.as_tensor(T, device=base.device)
+            K, U = Td @ K, Td @ U
+        cache[g] = engine.SharedProblem(K, err, self._D_host, self.omega.delta, variant=self.cost_function, device=base.device,
+                                        svd=self.svd, A_init=self.A_init, usv=(U, base.S, base.V), orthonormal_U=T is None)
+        return cache[g]
 
     def alpha_effective(self):
         """alpha * scale_alpha (python/maxent_loop.py:216-232)."""
@@ -213,13 +293,96 @@ class BatchedTauMaxEnt(object):
             return a * self.prepare().n_tau
         return a * float(self.scale_alpha)
 
-    def run_device(self, G_dev, want_A=True, want_v=False, D=None):
+    def run_device(self, G_dev, want_A=True, want_v=False, D=None, skip_small=False):
         """Hot path on device-resident data: returns an engine.SweepResult of device tensors.
-        ``D`` [B, n_omega] (optional): one default model per spectrum, incl. delta omega like ``DefaultModel.D``."""
+        ``D`` [B, n_omega] (optional): one default model per spectrum, incl. delta omega like ``DefaultModel.D``.
+        Per-spectrum error models (set_error / set_cov with a leading batch axis) are applied here.
+        ``skip_small``: spectra with max|G| < G_threshold are NOT continued (python/maxent_loop.py:174-179): they are left
+        out of the launch and come back with status MX_STATUS_SKIPPED, NaN scalars, alpha_index -1 and A = 0."""
+        import torch
+        if skip_small and G_dev.dim() > 1 and G_dev.shape[0]:
+            small = G_dev.abs().amax(dim=1) < self.G_threshold
+            if bool(small.any()):
+                return self._run_without(G_dev, small, want_A, want_v, D)
         prob = self.prepare()
-        return engine.run_sweep(prob, G_dev, self.alpha_effective(), probability=self.probability is not None,
-                                lm=self.minimizer, want_A=want_A, want_v=want_v, gamma=self.gamma,
-                                linefit_deg=self.linefit_deg, bryan_by_integration=self.bryan_by_integration, D=D)
+        kw = dict(probability=self.probability is not None, lm=self.minimizer, want_A=want_A, want_v=want_v,
+                  gamma=self.gamma, linefit_deg=self.linefit_deg, bryan_by_integration=self.bryan_by_integration, D=D)
+        B = int(G_dev.shape[0]) if G_dev.dim() > 1 else 1
+        mode, a, specs = self._error_plan(B)
+        if mode == "shared":
+            return engine.run_sweep(prob, G_dev, self.alpha_effective(), **kw)
+        if mode == "sigma":
+            return engine.run_sweep(prob, G_dev, self.alpha_effective(), sigma=a, **kw)
+        probs = [self._group_problem(g, spec) for g, spec in enumerate(specs)]
+        Gd = G_dev if G_dev.dim() > 1 else G_dev[None, :]
+        if any(spec[0] is not None for spec in specs):        # covariance groups: rotate the data, G' = T_g G
+            rows = max(q.n_tau for q in probs)
+            Gr = torch.zeros((B, rows), dtype=torch.float64, device=Gd.device)
+            idx = torch.as_tensor(a, device=Gd.device)
+            for g, (T, _) in enumerate(specs):
+                sel = torch.nonzero(idx == g).flatten()
+                if sel.numel():
+                    Gr[sel, :probs[g].n_tau] = Gd[sel] @ torch.as_tensor(T, device=Gd.device).T
+            Gd = Gr
+        alpha, scale = self.alpha_effective(), None
+        if isinstance(self.scale_alpha, str) and len(set(q.n_tau for q in probs)) > 1:
+            # scale_alpha = 'Ndata' counts the rows of the ROTATED data (python/maxent_loop.py:216-220, after set_cov):
+            # groups whose covariance dropped eigenvalues get their own factor
+            alpha = np.asarray(self.alpha_mesh, dtype=np.float64)
+            scale = np.array([probs[g].n_tau for g in a], dtype=np.float64)
+        elif isinstance(self.scale_alpha, str):
+            alpha = np.asarray(self.alpha_mesh, dtype=np.float64) * probs[0].n_tau
+        res = engine.run_sweep(probs[0], Gd, alpha, groups=(probs, a), alpha_scale=scale, **kw)
+        res.alpha_scale = scale
+        return res
+
+    def _run_without(self, G_dev, small, want_A, want_v, D):
+        """run_device on the spectra above the threshold, results scattered back into full-size tensors."""
+        import torch
+        B = int(G_dev.shape[0])
+        keep = torch.nonzero(~small).flatten()
+        kept = keep.cpu().numpy()
+        sub = BatchedTauMaxEnt.__new__(BatchedTauMaxEnt)
+        sub.__dict__.update(self.__dict__)                     # same kernel / problem caches, error model rows subset
+        if self.err is not None and np.ndim(self.err) >= 1 and np.shape(self.err)[0] == B and \
+                (np.ndim(self.err) == 2 or self._per_spectrum or B != self.prepare().n_tau):
+            sub.err = np.asarray(self.err)[kept]
+        if getattr(self, "cov", None) is not None and self.cov.ndim == 3:
+            sub.cov = self.cov[kept]
+        Dk = None if D is None else (D[keep] if torch.is_tensor(D) else np.asarray(D)[kept])
+        r = sub.run_device(G_dev[keep].contiguous(), want_A=want_A, want_v=want_v, D=Dk) if keep.numel() else None
+        prob = self.prepare()
+        dev = prob.device
+        n_alpha = len(self.alpha_mesh)
+        full = engine.SweepResult()
+        full.alpha = torch.as_tensor(self.alpha_effective(), device=dev) if r is None else r.alpha
+        full.n_sv = prob.n_sv
+        full.alpha_scale = None
+
+        def blank(shape, dtype, fill):
+            return torch.full((B,) + shape, fill, dtype=dtype, device=dev)
+        f64, i32 = torch.float64, torch.int32
+        spec = dict(chi2=((n_alpha,), f64, float("nan")), S=((n_alpha,), f64, float("nan")), Q=((n_alpha,), f64, float("nan")),
+                    logp=((n_alpha,), f64, float("nan")), n_iter=((n_alpha,), i32, 0), n_qeval=((n_alpha,), i32, 0),
+                    n_solve=((n_alpha,), i32, 0), status=((n_alpha,), i32, _lib.STATUS_SKIPPED), n_trial=((n_alpha,), i32, 0),
+                    n_batch=((n_alpha,), i32, 0), alpha_index=((_lib.N_ANALYZERS,), i32, -1))
+        for name, (shape, dtype, fill) in spec.items():
+            t = blank(shape, dtype, fill)
+            if r is not None and getattr(r, name) is not None:
+                t[keep] = getattr(r, name)
+            setattr(full, name, t)
+        for name, shape in (("A", (n_alpha, prob.n_omega)), ("A_out", (_lib.N_ANALYZERS, prob.n_omega)), ("v", (n_alpha, prob.n_sv))):
+            src = None if r is None else getattr(r, name)
+            want = want_A if name != "v" else want_v
+            if not want:
+                setattr(full, name, None)
+                continue
+            t = blank(shape, f64, 0.0)
+            if src is not None:
+                t[keep] = src
+            setattr(full, name, t)
+        full.phase_cycles = None
+        return full
 
     def time_sweep_kernel(self, G_dev):
         """Milliseconds of the mx_alpha_sweep launch alone (CUDA events on the launching stream)."""
@@ -243,9 +406,9 @@ class BatchedTauMaxEnt(object):
         out.h2d_bytes = Gt.numel() * 8 if not Gt.is_cuda else 0
         with torch.cuda.device(dev):
             G_dev = Gt.to(dev, non_blocking=True)
-            res = self.run_device(G_dev, D=D)
-            # spectra below the threshold are not continued by the reference (maxent_loop.py:174-179)
-            small = (G_dev.abs().amax(dim=1) < self.G_threshold) if G_dev.shape[0] else None
+            # spectra below the threshold are not continued by the reference (maxent_loop.py:174-179): skip_small
+            res = self.run_device(G_dev, D=D, skip_small=True)
+            small = ((res.status[:, 0] & _lib.STATUS_SKIPPED) != 0) if G_dev.shape[0] else None
             host = {}
             n_d2h = 0
             for name, t in (("chi2", res.chi2), ("S", res.S), ("Q", res.Q), ("probability", res.logp),
@@ -267,8 +430,6 @@ class BatchedTauMaxEnt(object):
             setattr(out, name, host[name].numpy())
         out.converged = (host["status"].numpy() & _lib.STATUS_CONVERGED).astype(bool)
         out.zero_elements = [] if host["small"] is None else np.nonzero(host["small"].numpy())[0].tolist()
-        for b in out.zero_elements:
-            out.A_out[b] = 0.0
         out.n_sv = prob.n_sv
         return out
 

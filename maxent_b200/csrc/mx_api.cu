@@ -304,8 +304,13 @@ static int fill_args(const MxProblem* p, SweepArgs& a) {
     a.mu0 = p->lm.mu0; a.nu = p->lm.nu; a.max_mu = p->lm.max_mu;
     a.conv_maxd = p->lm.conv_max_derivative; a.conv_relq = p->lm.conv_rel_change; a.eta = p->chi2_factor;
     a.conv_absq = p->lm.conv_abs_change; a.marquardt = p->lm.marquardt ? 1 : 0;
-    a.per_spec = p->per_spectrum_model ? 1 : 0;
+    a.per_spec = (p->per_spectrum_model & MX_PER_SPECTRUM_MODEL) ? 1 : 0;
+    a.per_spec_xi = (p->per_spectrum_model & MX_PER_SPECTRUM_XI) ? 1 : 0;
+    a.per_spec_alpha = (p->per_spectrum_model & MX_PER_SPECTRUM_ALPHA) ? 1 : 0;
     a.Vt = p->Vt; a.D = p->D; a.delta = p->delta; a.xi = p->xi; a.alpha = p->alpha; a.v0 = p->v0;
+    a.vt_index = (p->per_spectrum_model & MX_PER_SPECTRUM_VT) ? p->vt_index : nullptr;
+    a.vt_stride = p->vt_stride;
+    if ((p->per_spectrum_model & MX_PER_SPECTRUM_VT) && (!p->vt_index || p->vt_stride < 1)) return MX_ERR_BAD_ARG;
     return MX_OK;
 }
 
@@ -332,7 +337,9 @@ int64_t mx_sweep_workspace_bytes(const MxProblem* p, int32_t B) {
     SweepArgs a = {};
     a.n_sv = p->n_sv;
     a.B = B > 0 ? B : 1;
-    a.per_spec = p->per_spectrum_model ? 1 : 0;
+    a.per_spec = (p->per_spectrum_model & MX_PER_SPECTRUM_MODEL) ? 1 : 0;
+    a.per_spec_xi = (p->per_spectrum_model & MX_PER_SPECTRUM_XI) ? 1 : 0;
+    a.per_spec_alpha = (p->per_spectrum_model & MX_PER_SPECTRUM_ALPHA) ? 1 : 0;
     a.marquardt = p->lm.marquardt ? 1 : 0;
     a.conv_absq = p->lm.conv_abs_change;
     int eng = 0, grid = 0;

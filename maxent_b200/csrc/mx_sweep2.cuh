@@ -653,13 +653,13 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     for (int i = tid; i < SP; i += NTHR) {
-        const double x = i < s ? a.xi[i] : 0.0;
+        const double x = (i < s && !a.per_spec_xi) ? a.xi[i] : 0.0;
         sm[LY::o_xi + i] = x;
         sm[LY::o_lam + i] = x * x;
     }
     __syncthreads();
 
-    const Pipe<NT> pipe{sm + LY::o_stage, a.Vt, bar_full, bar_empty, tid, lane, n_kt, nch};
+    Pipe<NT> pipe{sm + LY::o_stage, a.Vt, bar_full, bar_empty, tid, lane, n_kt, nch};
     const double* Dsp = a.D;
     // phase timers: thread 0 charges the cycles since the previous tick to phase k (only when the caller asked
     // for them: MxSweepOut.phase_cycles)
@@ -1004,11 +1004,17 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
         const int sp = ctl.spec;
         if (sp >= a.B) break;
         Dsp = a.D + (a.per_spec ? (size_t)sp * ((a.n_omega + 1) & ~1) : 0);       // per-spectrum default model (Poorman off-diagonals)
+        if (a.vt_index) pipe.Vt = a.Vt + (size_t)a.vt_index[sp] * (size_t)a.vt_stride;   // the V' of this spectrum's whitening group
         const double* const v0sp = a.v0 + (a.per_spec ? (size_t)sp * s : 0);
         for (int i = tid; i < SP; i += NTHR) {
             const double v0 = i < s ? v0sp[i] : 0.0;
             sm[LY::o_v + i] = v0;
             sm[LY::o_gt + i] = i < s ? a.gt[(size_t)sp * s + i] : 0.0;
+            if (a.per_spec_xi) {             // per-spectrum error scale: Xi_b = S / sigma_b (python/tau_maxent.py:227-251 per data set)
+                const double x = i < s ? a.xi[(size_t)sp * s + i] : 0.0;
+                sm[LY::o_xi + i] = x;
+                sm[LY::o_lam + i] = x * x;
+            }
         }
         for (int i = tid; i < MAXB * SP; i += NTHR) {
             const int b = i / SP, j = i - b * SP;
@@ -1016,7 +1022,7 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
         }
         if (tid == 0) {
             ctl.ia = 0; ctl.it = 0; ctl.nq = 0; ctl.ns = 0; ctl.dir_up = 1; ctl.last_len = 99; ctl.ntrial = 1; ctl.nbatch = 1;
-            ctl.alpha = a.alpha[0]; ctl.c0 = a.c0[sp];
+            ctl.alpha = a.alpha[a.per_spec_alpha ? (size_t)sp * a.n_alpha : 0]; ctl.c0 = a.c0[sp];
             ctl.lm.mu = a.mu0; ctl.lm.Q0 = nan(""); ctl.lm.phase = PH_FIRST;
             ctl.nuniq = 1; ctl.nb = 0; ctl.urow[0] = 0; ctl.ufail[0] = 0;
         }
@@ -1085,7 +1091,7 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
                 if (tid == 0) {
                     ctl.ia++;
                     if (ctl.ia < a.n_alpha) {
-                        ctl.alpha = a.alpha[ctl.ia];
+                        ctl.alpha = a.alpha[(a.per_spec_alpha ? (size_t)sp * a.n_alpha : 0) + ctl.ia];
                         ctl.lm.mu = a.mu0; ctl.lm.Q0 = nan(""); ctl.it = 0; ctl.nq = 1; ctl.ns = 0; ctl.dir_up = 1; ctl.last_len = 99;
                         ctl.ntrial = 0; ctl.nbatch = 0;
                     }

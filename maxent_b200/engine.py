@@ -287,7 +287,7 @@ def svd_jacobi_host(K, device=None):
 class SweepResult(object):
     """Device tensors produced by one call of the fused sweep (+ analyzers)."""
     __slots__ = ("alpha", "v", "A", "chi2", "S", "Q", "logp", "n_iter", "n_qeval", "n_solve", "status",
-                 "alpha_index", "A_out", "n_sv", "n_trial", "n_batch", "phase_cycles")
+                 "alpha_index", "A_out", "n_sv", "n_trial", "n_batch", "phase_cycles", "alpha_scale")
 
 
 def _stream(dev):
@@ -303,25 +303,44 @@ def _dev_f64(x, dev):
     return torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64), device=dev)
 
 
-def _problem_struct(prob, alpha, probability, lm, chi2_factor, D_rows=None, v0_rows=None):
-    per = D_rows is not None
+class _Rows(object):
+    """Per-spectrum overrides of the shared problem state (MxProblem.per_spectrum_model bits): default models and
+    initial vectors, error scales (xi rows), whitening groups (stacked V' buffers + index)."""
+    __slots__ = ("D", "v0", "xi", "Vt", "vt_index", "vt_stride", "alpha")
+
+    def __init__(self, D=None, v0=None, xi=None, Vt=None, vt_index=None, vt_stride=0, alpha=None):
+        self.D, self.v0, self.xi, self.Vt, self.vt_index, self.vt_stride = D, v0, xi, Vt, vt_index, vt_stride
+        self.alpha = alpha
+
+    def flags(self):
+        return ((_lib.PER_SPECTRUM_MODEL if self.D is not None else 0) | (_lib.PER_SPECTRUM_XI if self.xi is not None else 0)
+                | (_lib.PER_SPECTRUM_VT if self.vt_index is not None else 0)
+                | (_lib.PER_SPECTRUM_ALPHA if self.alpha is not None else 0))
+
+
+def _problem_struct(prob, alpha, probability, lm, chi2_factor, rows=None):
+    r = rows or _Rows()
+    per = r.D is not None
     return _lib.MxProblem(prob.n_tau, prob.n_omega, prob.n_sv, int(alpha.numel()), _lib.VARIANTS[prob.variant],
-                          int(bool(probability)), int(getattr(prob, "engine", 0)), int(per), float(chi2_factor),
-                          _ptr(prob.Vt), _ptr(prob.Qw), _ptr(prob.Q), _ptr(prob.sqrtw), _ptr(prob.xi),
-                          _ptr(D_rows if per else prob.D), _ptr(prob.delta), _ptr(alpha),
-                          _ptr(v0_rows if per else prob.v0), lm.c_struct())
+                          int(bool(probability)), int(getattr(prob, "engine", 0)), r.flags(), float(chi2_factor),
+                          _ptr(prob.Vt if r.Vt is None else r.Vt), _ptr(prob.Qw), _ptr(prob.Q), _ptr(prob.sqrtw),
+                          _ptr(prob.xi if r.xi is None else r.xi), _ptr(r.D if per else prob.D), _ptr(prob.delta),
+                          _ptr(alpha if r.alpha is None else r.alpha),
+                          _ptr(r.v0 if per else prob.v0), lm.c_struct(), _ptr(r.vt_index), int(r.vt_stride))
 
 
-def _problem_args(prob, alpha, probability, lm, chi2_factor, D_rows=None, v0_rows=None):
+def _problem_args(prob, alpha, probability, lm, chi2_factor, rows=None):
     """The same problem description as the leading arguments of the torch operators (maxent_b200/ops.py)."""
-    per = D_rows is not None
+    r = rows or _Rows()
+    per = r.D is not None
     dims = [prob.n_tau, prob.n_omega, prob.n_sv, int(alpha.numel()), _lib.VARIANTS[prob.variant],
-            int(bool(probability)), int(getattr(prob, "engine", 0)), int(per), int(lm.maxiter), int(lm.miniter),
-            int(lm.marquardt)]
+            int(bool(probability)), int(getattr(prob, "engine", 0)), r.flags(), int(lm.maxiter), int(lm.miniter),
+            int(lm.marquardt), int(r.vt_stride)]
     params = [float(chi2_factor), float(lm.mu0), float(lm.nu), float(lm.max_mu), float(lm.conv_max_derivative),
               float(lm.conv_rel_change), float(lm.conv_abs_change)]
-    return (prob.Vt, prob.Qw, prob.Q, prob.sqrtw, prob.xi, D_rows if per else prob.D, prob.delta, alpha,
-            v0_rows if per else prob.v0, dims, params)
+    return (prob.Vt if r.Vt is None else r.Vt, prob.Qw, prob.Q, prob.sqrtw, prob.xi if r.xi is None else r.xi,
+            r.D if per else prob.D, prob.delta, alpha if r.alpha is None else r.alpha, r.v0 if per else prob.v0, r.vt_index,
+            dims, params)
 
 
 def _ops():
@@ -395,10 +414,18 @@ def analyze(alpha, chi2, S, logp, A, gamma=0.2, linefit_deg=0, bryan_by_integrat
 
 def run_sweep(prob, G, alpha_eff, probability=False, lm=None, chi2_factor=1.0, want_A=True, want_v=True,
               analyze_results=True, gamma=0.2, linefit_deg=0, bryan_by_integration=False, time_kernel=False, D=None,
-              phase_timers=False):
+              phase_timers=False, sigma=None, groups=None, alpha_scale=None):
     """Fused alpha sweep for a batch G[B, n_tau] sharing `prob`.  `alpha_eff` = alpha * scale_alpha, descending.
     G may live on the host (numpy / pinned tensor: copied asynchronously) or on the device.
-    Everything stays on the device; returns a SweepResult of torch tensors."""
+    Everything stays on the device; returns a SweepResult of torch tensors.
+
+    Error models per spectrum (TauMaxEnt.set_error / set_cov per data set, python/tau_maxent.py:227-288), still ONE
+    launch of the sweep: ``sigma`` [B] gives every spectrum its own scalar error bar (``prob`` built with err = 1);
+    ``groups`` = (problems, index[B]) gives every spectrum one of several SharedProblems that differ in the error vector
+    or covariance (hence in the whitening rotation V'); G[b] is then the data of spectrum b in the (rotated) data space
+    of its group, rows padded to the longest.  ``prob`` must be problems[0].  ``alpha_scale`` [B] (with ``groups``)
+    multiplies the alpha mesh per spectrum (scale_alpha = 'Ndata' when groups keep different numbers of data rows; the
+    analyzers are invariant under a common factor on alpha and see the unscaled mesh)."""
     torch = _torch()
     lib = prob.lib
     dev = prob.device
@@ -409,21 +436,57 @@ def run_sweep(prob, G, alpha_eff, probability=False, lm=None, chi2_factor=1.0, w
         if G.dim() == 1:
             G = G[None, :]
         B = int(G.shape[0])
-        if G.shape[1] != prob.n_tau:
-            raise ValueError("G has %d data points, kernel has %d" % (G.shape[1], prob.n_tau))
         alpha = _dev_f64(np.asarray(alpha_eff, dtype=np.float64) if not torch.is_tensor(alpha_eff) else alpha_eff, dev)
         n_alpha, s, n_omega = int(alpha.numel()), prob.n_sv, prob.n_omega
-        D_rows = v0_rows = None
-        if D is not None:                    # one default model per spectrum, D[B, n_omega]
-            D_rows, v0_rows = per_spectrum_models(prob, D, getattr(prob, "A_init_host", None))
-            if D_rows.shape[0] != B:
-                raise ValueError("D has %d rows for %d spectra" % (D_rows.shape[0], B))
+        rows = _Rows()
         ops = _ops()
-        p = _problem_struct(prob, alpha, probability, lm, chi2_factor, D_rows, v0_rows)
-        pargs = _problem_args(prob, alpha, probability, lm, chi2_factor, D_rows, v0_rows)
         gt = torch.empty((B, s), dtype=f64, device=dev)
         c0 = torch.empty((B,), dtype=f64, device=dev)
-        ops.project_data(*pargs, G, gt, c0)
+        if groups is not None:
+            probs, index = groups
+            index = torch.as_tensor(np.asarray(index) if not torch.is_tensor(index) else index, device=dev).to(torch.int64)
+            if probs[0] is not prob or any(q.n_sv != s or q.n_omega != n_omega or q.variant != prob.variant for q in probs):
+                raise ValueError("the problems of all groups must share kernel, cut and cost function")
+            if D is not None:
+                raise ValueError("per-spectrum default models and error groups cannot be combined yet")
+            nvt = max(int(q.Vt.numel()) for q in probs)
+            rows.Vt = torch.zeros((len(probs), nvt), dtype=f64, device=dev)
+            for g, q in enumerate(probs):
+                rows.Vt[g, :q.Vt.numel()] = q.Vt
+            rows.vt_index, rows.vt_stride = index.to(torch.int32).contiguous(), nvt
+            if alpha_scale is not None:          # alpha * (data rows of the spectrum's group), python/maxent_loop.py:216-220
+                rows.alpha = (alpha[None, :] * _dev_f64(alpha_scale, dev).reshape(-1, 1)).contiguous()
+            rows.xi = torch.stack([q.xi for q in probs])[index].contiguous()
+            rows.v0 = torch.stack([q.v0 for q in probs])[index].contiguous()
+            ld = (n_omega + 1) & ~1
+            rows.D = torch.zeros((B, ld), dtype=f64, device=dev)
+            rows.D[:, :n_omega] = prob.D
+            for g, q in enumerate(probs):              # projection per group: its own Q, 1/err and row count
+                sel = torch.nonzero(index == g).flatten()
+                if sel.numel() == 0:
+                    continue
+                Gg = G[sel][:, :q.n_tau].contiguous()
+                gg = torch.empty((sel.numel(), s), dtype=f64, device=dev)
+                cg = torch.empty((sel.numel(),), dtype=f64, device=dev)
+                ops.project_data(*_problem_args(q, alpha, False, lm, chi2_factor), Gg, gg, cg)
+                gt[sel] = gg
+                c0[sel] = cg
+        else:
+            if G.shape[1] != prob.n_tau:
+                raise ValueError("G has %d data points, kernel has %d" % (G.shape[1], prob.n_tau))
+            if D is not None:                    # one default model per spectrum, D[B, n_omega]
+                rows.D, rows.v0 = per_spectrum_models(prob, D, getattr(prob, "A_init_host", None))
+                if rows.D.shape[0] != B:
+                    raise ValueError("D has %d rows for %d spectra" % (rows.D.shape[0], B))
+            if sigma is not None:                # Xi_b = Xi / sigma_b, data divided by sigma_b (prob carries err = 1)
+                sg = _dev_f64(sigma, dev).reshape(-1)
+                if sg.numel() != B:
+                    raise ValueError("sigma has %d entries for %d spectra" % (sg.numel(), B))
+                rows.xi = (prob.xi[None, :] / sg[:, None]).contiguous()
+                G = (G / sg[:, None]).contiguous()
+            ops.project_data(*_problem_args(prob, alpha, False, lm, chi2_factor), G, gt, c0)
+        p = _problem_struct(prob, alpha, probability, lm, chi2_factor, rows)
+        pargs = _problem_args(prob, alpha, probability, lm, chi2_factor, rows)
         r = SweepResult()
         r.alpha = alpha
         r.n_sv = s

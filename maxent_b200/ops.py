@@ -20,10 +20,10 @@ import torch
 from . import _lib
 
 # dims  = [n_tau, n_omega, n_sv, n_alpha, variant, want_probability, engine, per_spectrum_model, maxiter, miniter,
-#          marquardt]
+#          marquardt, vt_stride]
 # param = [chi2_factor, mu0, nu, max_mu, conv_max_derivative, conv_rel_change, conv_abs_change]
 _PROBLEM = ("Tensor Vt, Tensor Qw, Tensor Qo, Tensor sqrtw, Tensor xi, Tensor D, Tensor delta, Tensor alpha, "
-            "Tensor v0, int[] dims, float[] params")
+            "Tensor v0, Tensor? vt_index, int[] dims, float[] params")
 
 _library = torch.library.Library("maxent_b200", "DEF")
 _library.define("project_data(" + _PROBLEM + ", Tensor G, Tensor(a!) gt, Tensor(b!) c0) -> ()")
@@ -49,28 +49,30 @@ def _f64c(*ts):
             raise ValueError("maxent_b200 operators take contiguous float64 tensors")
 
 
-def _problem(Vt, Qw, Qo, sqrtw, xi, D, delta, alpha, v0, dims, params):
-    if len(dims) != 11 or len(params) != 7:
-        raise ValueError("dims must hold 11 integers and params 7 floats (see maxent_b200/ops.py)")
+def _problem(Vt, Qw, Qo, sqrtw, xi, D, delta, alpha, v0, vt_index, dims, params):
+    if len(dims) != 12 or len(params) != 7:
+        raise ValueError("dims must hold 12 integers and params 7 floats (see maxent_b200/ops.py)")
+    if vt_index is not None and (vt_index.dtype != torch.int32 or not vt_index.is_contiguous()):
+        raise ValueError("vt_index must be a contiguous int32 tensor")
     _f64c(Vt, Qw, Qo, sqrtw, xi, D, delta, alpha, v0)
     lm = _lib.MxLMParams(int(dims[8]), int(dims[9]), float(params[1]), float(params[2]), float(params[3]),
                          float(params[4]), float(params[5]), float(params[6]), int(dims[10]), 0)
     return _lib.MxProblem(int(dims[0]), int(dims[1]), int(dims[2]), int(dims[3]), int(dims[4]), int(dims[5]),
                           int(dims[6]), int(dims[7]), float(params[0]), _ptr(Vt), _ptr(Qw), _ptr(Qo), _ptr(sqrtw),
-                          _ptr(xi), _ptr(D), _ptr(delta), _ptr(alpha), _ptr(v0), lm)
+                          _ptr(xi), _ptr(D), _ptr(delta), _ptr(alpha), _ptr(v0), lm, _ptr(vt_index), int(dims[11]))
 
 
-def _project_data(Vt, Qw, Qo, sqrtw, xi, D, delta, alpha, v0, dims, params, G, gt, c0):
-    p = _problem(Vt, Qw, Qo, sqrtw, xi, D, delta, alpha, v0, dims, params)
+def _project_data(Vt, Qw, Qo, sqrtw, xi, D, delta, alpha, v0, vt_index, dims, params, G, gt, c0):
+    p = _problem(Vt, Qw, Qo, sqrtw, xi, D, delta, alpha, v0, vt_index, dims, params)
     _f64c(G, gt, c0)
     with torch.cuda.device(G.device):
         _lib.check(_lib.load().mx_project_data(ctypes.byref(p), _ptr(G), int(G.shape[0]), _ptr(gt), _ptr(c0),
                                                _stream(G)), "mx_project_data")
 
 
-def _alpha_sweep(Vt, Qw, Qo, sqrtw, xi, D, delta, alpha, v0, dims, params, gt, c0, v, A, chi2, S, Q, logp,
+def _alpha_sweep(Vt, Qw, Qo, sqrtw, xi, D, delta, alpha, v0, vt_index, dims, params, gt, c0, v, A, chi2, S, Q, logp,
                  n_iter, n_qeval, n_solve, status, n_trial, n_batch, phase_cycles, workspace):
-    p = _problem(Vt, Qw, Qo, sqrtw, xi, D, delta, alpha, v0, dims, params)
+    p = _problem(Vt, Qw, Qo, sqrtw, xi, D, delta, alpha, v0, vt_index, dims, params)
     _f64c(gt, c0, v, A, chi2, S, Q, logp)
     out = _lib.MxSweepOut(_ptr(v), _ptr(A), _ptr(chi2), _ptr(S), _ptr(Q), _ptr(logp), _ptr(n_iter), _ptr(n_qeval),
                           _ptr(n_solve), _ptr(status), _ptr(n_trial), _ptr(n_batch), _ptr(phase_cycles))

@@ -114,5 +114,5 @@ def test_torch_operators_registered_cuda_only():
         ops.analyze(t[0], t, t, None, None, 0.2, 0, False, torch.zeros((1, 5), dtype=torch.int32), None, None)
     z = torch.zeros(4, dtype=torch.float64)
     with pytest.raises(NotImplementedError):
-        ops.project_data(z, z, z, z, z, z, z, z, z, [2, 2, 2, 1, 0, 0, 0, 0, 10, 0, 0], [1.0, 1e-18, 1.3, 1e20, 1e-4, 1e-16, -1.0],
+        ops.project_data(z, z, z, z, z, z, z, z, z, None, [2, 2, 2, 1, 0, 0, 0, 0, 10, 0, 0, 0], [1.0, 1e-18, 1.3, 1e20, 1e-4, 1e-16, -1.0],
                          t, t, z)

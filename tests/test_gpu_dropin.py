@@ -353,6 +353,135 @@ def test_rank_above_the_fused_limit_raises():
     assert prob.n_sv == 64 and prob.n_sv_uncapped == 100
 
 
+def test_per_spectrum_error_models_in_one_launch():
+    """BatchedTauMaxEnt with an error model PER SPECTRUM (TauMaxEnt.set_error / set_cov are per data set in the
+    reference, python/tau_maxent.py:227-288; test/python/cov.py:53-90): one scalar sigma per spectrum, one error vector
+    per spectrum (three distinct vectors -> three whitening groups in ONE launch of the sweep), one covariance matrix
+    per spectrum.  Every spectrum against the oracle run with its own error model, tiered contract."""
+    from maxent_b200 import batched
+    pr = mo.synthetic_problem(120, 60, beta=20.0, mu=[0.5, -0.5, 1.0, 0.0, 0.8, -0.2], sigma=1e-3, seed=3)
+    n_tau, B = 120, 6
+    mesh = mo.log_alpha_mesh(0.5, 500.0, 8)
+    rng = np.random.RandomState(8)
+
+    def job():
+        j = batched.BatchedTauMaxEnt(reduce_singular_space=1e-10)
+        j.set_kernel_tau(pr["tau"], batched.DataOmegaMesh(pr["omega"]), beta=20.0)
+        j.alpha_mesh = mb.DataAlphaMesh(mesh)
+        return j
+
+    def check(out, b, o, what):
+        o2 = o["rerun"]
+        tol = np.maximum(1e-8, 10 * gc.running_max(gc.rel_A(o2["A"], o["A"])))
+        dA = gc.rel_A(out.A(b), o["A"])
+        assert np.all(dA <= tol), (what, b, dA / tol)
+        np.testing.assert_allclose(out.chi2[b], o["chi2"], rtol=1e-7, err_msg="%s %d" % (what, b))
+        assert int(out.alpha_index[b, 0]) == o["analyzers"]["LineFitAnalyzer"]["alpha_index"], (what, b)
+        assert int(out.alpha_index[b, 1]) == o["analyzers"]["Chi2CurvatureAnalyzer"]["alpha_index"], (what, b)
+
+    def oracle(K, G, err, svd=None):
+        o = mo.maxent_loop(K, G, err, pr["omega"], mesh, reduce_singular_space=1e-10, svd=svd)
+        o["rerun"] = mo.maxent_loop(K, G * (1 + 1e-15), err, pr["omega"], mesh, reduce_singular_space=1e-10, svd=svd, analyzers=False)
+        return o
+
+    # (a) one scalar error bar per spectrum
+    sig = np.array([1e-3, 2e-3, 5e-4, 1e-3, 3e-3, 5e-4])
+    j = job()
+    j.set_error(sig)
+    out = j.run(pr["G"])
+    for b in range(B):
+        check(out, b, oracle(pr["K"], pr["G"][b], sig[b]), "sigma")
+    # (b) one error vector per spectrum, three distinct ones
+    vecs = 1e-3 * (1.0 + 0.5 * rng.rand(3, n_tau))
+    which = np.array([0, 1, 2, 1, 0, 2])
+    j = job()
+    j.set_error(vecs[which])
+    out = j.run(pr["G"])
+    mode, index, specs = j._error_plan(B)
+    assert mode == "groups" and len(specs) == 3
+    for b in range(B):
+        check(out, b, oracle(pr["K"], pr["G"][b], vecs[which[b]]), "vector")
+    # (c) one covariance matrix per spectrum (two distinct ones, the second rank deficient -> fewer rotated rows)
+    i = np.arange(n_tau)
+    C0 = 1e-6 * (np.eye(n_tau) + 0.4 * np.exp(-np.abs(i[:, None] - i[None, :]) / 2.5))
+    Bm = rng.randn(n_tau, 90)
+    C1 = 4e-6 * (Bm @ Bm.T) / 90
+    covs = np.stack([C0, C1, C0, C1, C1, C0])
+    j = job()
+    j.set_cov(covs)
+    out = j.run(pr["G"])
+    U0, S0, V0 = mo.kernel_svd(pr["K"], 1e-10)
+    for b in range(B):
+        e, v = np.linalg.eigh(covs[b])
+        keep = e >= 1e-14
+        T = v[:, keep].T
+        check(out, b, oracle(T @ pr["K"], T @ pr["G"][b], np.sqrt(e[keep]), svd=(T @ U0, S0, V0)), "cov")
+
+
+def test_config4_matches_reference_run():
+    """BASELINE config 4 (n_tau = 10000, n_omega = 2000, 100 alphas, probability, cut 1e-11) against the run of the REAL
+    reference stored in tests/golden/g13 (218 s on 8 cores + its reproducibility run): chi2, S, Q, probability for all 100
+    alphas and A at the analyzer picks and every tenth alpha under the tiered contract, identical picks."""
+    g = gc.load_golden("g13_config4_10000x2000.npz")
+    pr = mo.synthetic_problem(10000, 2000, mu=1.0, seed=1234)
+    G = pr["G"][0]
+    assert abs(float(np.sum(G)) - float(g["G_sha_check"])) < 1e-9
+    tm = mb.TauMaxEnt(probability='normal', reduce_singular_space=1e-11)
+    tm.set_verbosity(mb.VerbosityFlags.Quiet)
+    tm.set_G_tau_data(pr["tau"], G)
+    tm.omega = mb.HyperbolicOmegaMesh(-10, 10, 2000)
+    tm.alpha_mesh = mb.LogAlphaMesh(0.01, 2000, 100)
+    tm.set_error(1e-4)
+    res = tm.run()
+    assert len(tm.K.S) == int(g["ref_n_sv"]) == 54
+    tolA, tolc, tolS = gc.tolerances(g, "A"), gc.tolerances(g, "chi2"), gc.tolerances(g, "S")
+    rows = g["A_rows"]
+    dA = gc.rel_A(res.A[rows], g["ref_A"])
+    assert np.all(dA <= tolA[rows]), (dA / tolA[rows])
+    dc = np.abs(res.chi2 / g["ref_chi2"] - 1)
+    assert np.all(dc <= np.maximum(tolc, 2e-7)), (dc / tolc).max()     # device TauKernel: see gc.check_against_reference
+    dQ = np.abs(res.Q / g["ref_Q"] - 1)
+    assert np.all(dQ <= np.maximum(tolc, tolS)), dQ.max()
+    p, pref = res.probability, g["ref_probability"]
+    assert np.all(np.abs(p - pref) <= np.maximum(gc.PROB_RTOL, gc.NOISE_FACTOR * gc.running_max(g["noise_chi2"])) * np.abs(pref))
+    for name in ('LineFitAnalyzer', 'Chi2CurvatureAnalyzer', 'EntropyAnalyzer', 'ClassicAnalyzer'):
+        assert res.analyzer_results[name]['alpha_index'] == int(g["ref_idx_" + name]), name
+        k = int(g["ref_idx_" + name])
+        ref = g["ref_Aout_" + name]
+        assert np.max(np.abs(res.analyzer_results[name]['A_out'] - ref)) <= tolA[k] * np.max(np.abs(ref)), name
+
+
+def test_batched_threshold_skip_on_the_device():
+    """max|G| < G_threshold (python/maxent_loop.py:174-179) in a batch: such spectra are left out of the launch, come back
+    with MX_STATUS_SKIPPED, NaN chi2, alpha_index -1 and A_out = 0 (device tensors as well as host arrays), and do not
+    change the other spectra by a bit; replacing a public attribute rebuilds the cached problem."""
+    import torch
+    from maxent_b200 import batched, _lib
+    pr = mo.synthetic_problem(120, 60, beta=20.0, mu=[0.5, -0.5, 1.0, 0.2], sigma=1e-3, seed=3)
+    j = batched.BatchedTauMaxEnt(reduce_singular_space=1e-10)
+    j.set_kernel_tau(pr["tau"], batched.DataOmegaMesh(pr["omega"]), beta=20.0)
+    j.set_alpha_mesh_log(0.5, 500.0, 6)
+    j.set_error(np.array([1e-3, 2e-3, 1e-3, 5e-4]))                # per-spectrum rows must follow the kept spectra
+    G = pr["G"].copy()
+    G[1] = 0.0
+    G[3] *= 1e-12
+    out = j.run(G)
+    assert out.zero_elements == [1, 3]
+    assert np.all(np.isnan(out.chi2[[1, 3]])) and np.all(out.alpha_index[[1, 3]] == -1) and np.all(out.A_out[[1, 3]] == 0.0)
+    assert bool((out.device.status[[1, 3]] == _lib.STATUS_SKIPPED).all()) and bool((out.device.A_out[[1, 3]] == 0).all())
+    assert not out.converged[1].any() and out.converged[0].all()
+    j2 = batched.BatchedTauMaxEnt(reduce_singular_space=1e-10)
+    j2.set_kernel_tau(pr["tau"], batched.DataOmegaMesh(pr["omega"]), beta=20.0)
+    j2.set_alpha_mesh_log(0.5, 500.0, 6)
+    j2.set_error(np.array([1e-3, 1e-3]))
+    ref = j2.run(G[[0, 2]])
+    np.testing.assert_array_equal(out.chi2[[0, 2]], ref.chi2)
+    np.testing.assert_array_equal(out.A_out[[0, 2]], ref.A_out)
+    p1 = j2.prepare()
+    j2.reduce_singular_space = 1e-8
+    assert j2.prepare() is not p1 and j2.prepare().n_sv < p1.n_sv
+
+
 def test_threshold_skip_and_unsupported_combinations():
     g = gc.load_golden("g2_synth_200x100.npz")
     tm = _tau_maxent_from_fixture(g)
