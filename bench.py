@@ -6,13 +6,16 @@
 A "step" is one pass of the hot path (data projection -> fused alpha sweep -> analyzers) over one
 synthetic bootstrap batch: per GPU, `--spectra` (default 8192 = BASELINE config 5's per-GPU shard of the
 65,536-spectrum batch) spectra with n_tau=2000, n_omega=1000, 60 alphas, reduce_singular_space=1e-11
-(SURVEY.md 8(d) C5 recipe).  Weak scaling: every rank owns its own shard, no data-path collective;
-one NCCL gather of the result arrays closes the e2e step.
+(SURVEY.md 8(d) C5 recipe).  Weak scaling: every rank owns its own shard, no data-path collective.
+The one collective of a multi-GPU job -- the NCCL gather of alpha_index / chi2 / A_out to rank 0 -- happens once per
+job, after the last step: it is timed separately (`config.final_gather_ms_once_per_job`) and `e2e_job` reports the
+throughput of a one-step job INCLUDING it.
 
 One JSON line is printed by rank 0 (see the contract in the task statement).  `value` = device-resident
 throughput, `e2e` = through the public batched API with pinned-host inputs/outputs, `roofline` = the
-sweep kernel's achieved algorithmic FP64 FLOP/s against the measured FP64 peak, `cpu_baseline` = the
-oracle port of the reference timed on the host cores in the same run (rank 0, N=1).
+sweep kernel's achieved algorithmic FP64 FLOP/s against the FP64 peak MEASURED IN THIS RUN (mx_fp64_peak: DMMA and DFMA
+saturating every SM, clocks sampled beside it), `cpu_baseline` = the oracle port of the reference timed on the host
+cores in the same run (rank 0, N=1).
 """
 import argparse
 import ctypes
@@ -28,11 +31,11 @@ sys.path.insert(0, ROOT)
 
 METRIC = "spectra/sec (full 60-alpha MaxEnt loop, FP64)"
 UNIT = "spectra/s"
-# Measured FP64 peak of this pool's B200 (tools/fp64_microbench.cu -> profiles/r01_fp64_microbench.json,
+# FP64 peak of this pool's B200 if the in-run measurement fails (tools/fp64_microbench.cu -> profiles/r01_fp64_microbench.json,
 # DMMA m8n8k4 and DFMA both saturate at 37.0 TFLOP/s).  MEASURED_PEAKS.json holds no FP64 figure.
 FP64_PEAK_FALLBACK_TFLOPS = 37.0
 # DRAM traffic of the sweep kernel from the ncu capture under profiles/ (bytes read + written, per spectrum)
-NCU_DRAM_BYTES_PER_SPECTRUM = int((3.665920e6 + 795.489024e6) / 296)   # profiles/r01c_sweep2_ncu_full_summary.json
+NCU_DRAM_BYTES_PER_SPECTRUM = int((3.449856e6 + 524.792832e6) / 296)   # profiles/r02a_sweep2_ncu_full_summary.json
 
 
 def parse_args():
@@ -219,6 +222,26 @@ def run_native(a):
 
     G_dev = G_host.to(dev)
     torch.cuda.synchronize()
+    import hashlib
+    g_sha = hashlib.sha256(G_host[:min(B, 64)].numpy().tobytes()).hexdigest()[:16]
+
+    # ---- FP64 peak of THIS device in THIS run (roofline denominator), clocks sampled while it runs --------------
+    peak_meas = None
+    try:
+        from maxent_b200 import _lib
+        lib = _lib.load()
+        scratch = torch.empty((2 * 148 * 256 * 2,), dtype=torch.float64, device=dev)
+        ps = ClockSampler(local)
+        ps.start()
+        t_dmma, t_dfma = ctypes.c_double(0.0), ctypes.c_double(0.0)
+        rc = lib.mx_fp64_peak(ctypes.byref(t_dmma), ctypes.byref(t_dfma), ctypes.c_void_p(scratch.data_ptr()),
+                              ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        pc = ps.stop()
+        if rc == 0 and t_dmma.value > 1.0:
+            peak_meas = {"dmma_tflops": t_dmma.value, "dfma_tflops": t_dfma.value, "sm_mhz": pc.get("sm_mhz"),
+                         "reasons": pc.get("reasons")}
+    except Exception as e:                      # keep the run alive, say so in the line
+        peak_meas = {"error": str(e)}
 
     def barrier():
         if world > 1:
@@ -251,7 +274,11 @@ def run_native(a):
     flops = algorithmic_flops(n_iter, n_q, n_s, B * a.n_alpha, a.n_omega, s, False)
     flops_survey = flops + n_q * 2.0 * a.n_tau * s
     peak = FP64_PEAK_FALLBACK_TFLOPS
-    peak_src = "measured FP64 DMMA/DFMA peak of this pool's B200, profiles/r01_fp64_microbench.json (MEASURED_PEAKS.json has no FP64 entry)"
+    peak_src = "fallback: FP64 DMMA/DFMA peak of this pool's B200 measured in round 1, profiles/r01_fp64_microbench.json"
+    if peak_meas and "dmma_tflops" in peak_meas:
+        peak = max(peak_meas["dmma_tflops"], peak_meas["dfma_tflops"])
+        peak_src = ("measured in this run on this device (mx_fp64_peak: every SM saturated with DMMA m8n8k4 / DFMA chains; "
+                    "MEASURED_PEAKS.json has no FP64 entry)")
     try:
         mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         for key in ("fp64_tflops", "dmma_tflops"):
@@ -273,6 +300,20 @@ def run_native(a):
     barrier()
     e2e_ms = e0.elapsed_time(e1)
     h2d, d2h = out.h2d_bytes, out.d2h_bytes
+
+    # ---- what the OPTIONAL copy of every A_alpha(omega) to the host would cost (the reference keeps them all in
+    #      memory; the batched API leaves them on the device: BatchedMaxEntResult.A(b)) -- measured once on a slice ----
+    nb_a = min(B, 1024)
+    a_pin = torch.empty((nb_a,) + tuple(out.device.A.shape[1:]), dtype=torch.float64, pin_memory=True)
+    torch.cuda.synchronize()
+    ea0, ea1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea0.record()
+    a_pin.copy_(out.device.A[:nb_a], non_blocking=True)
+    ea1.record()
+    torch.cuda.synchronize()
+    full_A_ms = ea0.elapsed_time(ea1) * (B / nb_a)
+    full_A_bytes = B * out.device.A.shape[1] * out.device.A.shape[2] * 8
+    del a_pin
 
     # ---- max over ranks -------------------------------------------------------------------------------
     gather_ms = 0.0
@@ -304,7 +345,9 @@ def run_native(a):
             "config": {"workload": workload_name(a), "n_sv": s, "parallelism": "spectra sharded x%d, no data-path collective" % world,
                        "l2": "inputs/outputs larger than L2 (G %.0f MB, A(alpha) %.1f GB per step); V' (%.0f KB) is L2-resident by design"
                              % (B * a.n_tau * 8 / 1e6, B * a.n_alpha * a.n_omega * 8 / 1e9, prob.Vt.numel() * 8 / 1e3),
-                       "final_gather_ms_once_per_job": round(gather_ms, 3),
+                       "final_gather_ms_once_per_job": round(gather_ms, 3), "G_sha256_first_64_rows": g_sha,
+                       "optional_full_A_alpha_d2h": {"bytes_per_step": full_A_bytes, "ms_per_step_extrapolated": round(full_A_ms, 1),
+                                                     "note": "not part of e2e: A_alpha stays on the device, e2e returns A_out of the five analyzers"},
                        "setup_s_once_per_kernel": round(setup_s, 3), "svd_sweeps": getattr(prob, "svd_sweeps", None),
                        "spectra_per_cta": prob.config["spectra_per_cta"], "smem_bytes": prob.config["smem_bytes"],
                        "lm_iterations_per_spectrum": n_iter / B, "q_evals_per_spectrum": n_q / B, "solves_per_spectrum": n_s / B,
@@ -315,13 +358,20 @@ def run_native(a):
                        "chi2curv_idx_hist": {int(k): int(v) for k, v in zip(*np.unique(idx[:, 1], return_counts=True))}},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / a.steps},
+            "e2e_job": {"value": world * B / ((e2e_ms / a.steps + gather_ms) * 1e-3), "unit": UNIT,
+                        "what": "one end-to-end step followed by the final gather of alpha_index / chi2 / A_out to rank 0 "
+                                "(a complete %d-spectrum job)" % (world * B)},
             "gpu_launches": a.steps * job.launches_per_step,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": NCU_DRAM_BYTES_PER_SPECTRUM * B, "traffic_unit": "bytes per launch",
                          "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one 296-spectrum "
-                                           "launch (profiles/), scaled to this launch's spectra; algorithmic bytes per spectrum = "
+                                           "launch (profiles/r02a_*), scaled to this launch's spectra; algorithmic bytes per spectrum = "
                                            "G in + A(alpha) out = %d" % (a.n_tau * 8 + a.n_alpha * a.n_omega * 8),
+                         "traffic_note": "accepted: %.1fx the algorithmic bytes -- the per-CTA scratch rows of w = dH/dx are written "
+                                         "through to HBM; the whole DRAM traffic of the kernel is ~0.1 %% of the HBM bandwidth "
+                                         "(FP64-pipe bound)" % (NCU_DRAM_BYTES_PER_SPECTRUM / (a.n_tau * 8 + a.n_alpha * a.n_omega * 8)),
+                         "peak_measured_in_run": peak_meas,
                          "kernel": "mx2::sweep2_kernel", "kernel_ms": kernel_ms,
                          "kernel_share_of_step": kernel_ms / (dev_ms / a.steps),
                          "flops_per_launch": flops, "flops_per_spectrum": flops / B,

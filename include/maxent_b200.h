@@ -133,6 +133,11 @@ typedef struct {
 int mx_device_sm_count(void);
 const char* mx_version(void);
 
+/* Measurement helper (bench.py): achieved FP64 TFLOP/s of the current device with every SM saturated by independent
+ * DMMA (mma.sync m8n8k4 f64) and by DFMA chains -- the roofline denominator of the sweep kernel, measured inside the
+ * benchmark run.  `scratch` = device buffer of at least 2 * SMs * 256 doubles.  Synchronous (returns host numbers). */
+int mx_fp64_peak(double* tflops_dmma_host, double* tflops_dfma_host, double* scratch, void* stream);
+
 /* Size in doubles of the swizzled V buffer for (n_omega, n_sv). */
 int64_t mx_layout_V_size(int32_t n_omega, int32_t n_sv);
 

@@ -55,6 +55,7 @@ class MxSweepOut(ctypes.Structure):
 SYMBOLS = [
     ("mx_version", ctypes.c_char_p, []),
     ("mx_device_sm_count", ctypes.c_int, []),
+    ("mx_fp64_peak", ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), c_dp, c_dp]),
     ("mx_layout_V_size", ctypes.c_int64, [ctypes.c_int32, ctypes.c_int32]),
     ("mx_layout_V", ctypes.c_int, [c_dp, ctypes.c_int32, ctypes.c_int32, c_dp, c_dp]),
     ("mx_tau_kernel", ctypes.c_int, [c_dp, c_dp, ctypes.c_int32, ctypes.c_int32, ctypes.c_double, c_dp, c_dp]),

@@ -16,7 +16,7 @@ Anything else (``d_dv=True``, ``dA_projection != 2``, foreign component classes)
 ``NotImplementedError`` when the loop runs: there is no generic host minimiser to fall back to."""
 import numpy as np
 
-from .functions import (NormalChi2, NormalEntropy, PlusMinusEntropy, NormalH_of_v, PlusMinusH_of_v,
+from .functions import (NormalChi2, ComplexChi2, NormalEntropy, PlusMinusEntropy, NormalH_of_v, PlusMinusH_of_v,
                         IdentityA_of_H, PreblurA_of_H)
 
 
@@ -55,8 +55,8 @@ class CostFunction(object):
     def _entropy_variant(self):
         s_tag = getattr(self._S, "variant_tag", None)
         h_tag = getattr(self._H_of_v, "variant_tag", None)
-        if not isinstance(self._chi2, NormalChi2) or not isinstance(self._A_of_H, (IdentityA_of_H, PreblurA_of_H)):
-            raise NotImplementedError("only NormalChi2 with IdentityA_of_H or PreblurA_of_H runs on the fused path")
+        if not isinstance(self._chi2, (NormalChi2, ComplexChi2)) or not isinstance(self._A_of_H, (IdentityA_of_H, PreblurA_of_H)):
+            raise NotImplementedError("only NormalChi2 / ComplexChi2 with IdentityA_of_H or PreblurA_of_H run on the fused path")
         if s_tag is None or s_tag != h_tag:
             raise NotImplementedError("entropy %s with parametrisation %s is not a fused variant (use Normal+Normal "
                                       "or PlusMinus+PlusMinus)" % (type(self._S).__name__, type(self._H_of_v).__name__))

@@ -227,6 +227,33 @@ __global__ void __launch_bounds__(128) analyze_kernel(const double* __restrict__
     }
 }
 
+// ---- measurement helper: FP64 pipe peak (the roofline denominator of the sweep kernel) --------------------------
+// Every SM runs 2 x 8 warps of independent DMMA (m8n8k4) or DFMA chains: what the FP64 pipe delivers when nothing else
+// limits it.  bench.py calls this inside the benchmark run (MEASURED_PEAKS.json carries no FP64 figure).
+template <bool MMA>
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, double a, double b, int iters) {
+    double c[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = threadIdx.x * 1e-3 + i;
+    for (int it = 0; it < iters; ++it) {
+        if (MMA) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                double acc[2] = {c[2 * i], c[2 * i + 1]};
+                dmma(acc, a, b);
+                c[2 * i] = acc[0]; c[2 * i + 1] = acc[1];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) c[i] = fma(c[i], a, b);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace mx
 
 using namespace mx;
@@ -273,6 +300,37 @@ int mx_svd_jacobi(const double* K, int32_t m, int32_t n, double* U, double* S, d
                   int32_t max_sweeps, int32_t* sweeps_done, void* stream) {
     if (!K || !U || !S || !V || !work || m < n || n < 1) return MX_ERR_BAD_ARG;
     return svd_jacobi(K, m, n, U, S, V, work, max_sweeps, sweeps_done, (cudaStream_t)stream);
+}
+
+int mx_fp64_peak(double* tflops_dmma, double* tflops_dfma, double* scratch, void* stream_) {
+    if (!tflops_dmma || !tflops_dfma || !scratch) return MX_ERR_BAD_ARG;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return MX_ERR_NO_DEVICE;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaEvent_t e0, e1;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return MX_ERR_CUDA;
+    const int grid = 2 * sms, iters = 1 << 15;
+    double best[2] = {0.0, 0.0};
+    for (int kind = 0; kind < 2; ++kind)
+        for (int rep = 0; rep < 4; ++rep) {          // first repetition warms up
+            cudaEventRecord(e0, stream);
+            if (kind == 0) fp64_peak_kernel<true><<<grid, 256, 0, stream>>>(scratch, 1e-3, 1e-3, iters);
+            else fp64_peak_kernel<false><<<grid, 256, 0, stream>>>(scratch, 1.0000001, 1e-9, iters);
+            cudaEventRecord(e1, stream);
+            if (cudaEventSynchronize(e1) != cudaSuccess) return MX_ERR_CUDA;
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            // flops per thread and iteration: 8 DMMA x 512 / 32 lanes = 128, or 16 FMA x 2 = 32
+            const double fl = (double)grid * 256 * iters * (kind == 0 ? 128.0 : 32.0);
+            const double tf = fl / (ms * 1e-3) / 1e12;
+            if (rep > 0 && tf > best[kind]) best[kind] = tf;
+        }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops_dmma = best[0];
+    *tflops_dfma = best[1];
+    return cudaGetLastError() == cudaSuccess ? MX_OK : MX_ERR_CUDA;
 }
 
 int64_t mx_svd_truncated_work_doubles(int32_t m, int32_t n, int32_t p) {

@@ -135,8 +135,10 @@ class NormalChi2(Chi2):
 
 
 class ComplexChi2(Chi2):
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError("ComplexChi2 is outside the fused FP64 path (SURVEY.md 8(f) rank 4)")
+    """chi2 = sum_i |G_i - sum_j K_ij H_j|^2 / sigma_i^2 for complex data and kernel (python/functions.py:380-437).  With
+    the real spectral functions of the fused path this is NormalChi2 on the stacked rows [Re; Im] (see
+    kernels.IOmegaKernel); the complex-A entropies of the reference are not on the fused path."""
+    variant_tag = "normal"
 
 
 # ---- entropies ------------------------------------------------------------------------------------

@@ -38,10 +38,16 @@ class KernelSVD(object):
         self._U = self._S = self._V = None
         self._svd_version += 1
 
+    def fused_matrix(self):
+        """The real matrix the fused path works with (and whose SVD ``svd`` returns): K itself for real kernels; complex
+        kernels stack real and imaginary rows (IOmegaKernel)."""
+        return np.asarray(self.K, dtype=np.float64)
+
     def svd(self):
         """Perform the SVD if not yet done; returns (U, S, V)."""
+        K = self.fused_matrix()                 # materialise first: a dirty kernel may (re)compute its SVD on the way
         if self._U is None:
-            self._U, self._S, self._V = _device_svd(np.asarray(self.K, dtype=np.float64))
+            self._U, self._S, self._V = _device_svd(K)
             self._svd_version += 1
         return self._U, self._S, self._V
 
@@ -196,11 +202,55 @@ class TauKernel(Kernel):
 
 
 class IOmegaKernel(Kernel):
-    """Matsubara-frequency kernel (python/kernels.py:283-346): complex data, outside the fused FP64 path
-    (SURVEY.md 8(f) rank 4)."""
+    """Matsubara-frequency kernel K(i omega_n, omega) = 1 / (i omega_n - omega)  (python/kernels.py:283-346):
+    G(i omega_n) = int d omega K A(omega); ``iomega`` is the REAL array of Matsubara frequencies, ``K`` and ``K_delta``
+    are complex like the reference's.
 
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError("IOmegaKernel (complex chi2) is not on the fused B200 path yet")
+    On the fused path the spectral function is real (Normal / PlusMinus / Bryan cost functions): the misfit
+    chi2 = sum_n |G_n - (K H)_n|^2 / sigma_n^2  (ComplexChi2.f, python/functions.py:401-404, for a real H) is the
+    NormalChi2 of the real system with the rows [Re K; Im K], [Re G; Im G], [sigma; sigma] -- ``fused_matrix`` returns
+    that stacked real matrix and ``U, S, V`` are ITS singular triplets (V real, U of 2 n rows), not those of the complex
+    matrix.  The complex-A formalism of the reference (ComplexPlusMinusEntropy / ComplexPlusMinusH_of_v) is not on the
+    fused path."""
+
+    is_complex = True
+
+    def __init__(self, iomega, omega, beta=None):
+        super(IOmegaKernel, self).__init__()
+        self.iomega = np.asarray(iomega, dtype=np.float64)
+        self.omega = omega
+        self.beta = beta
+        self._fill_values()
+
+    def _fill_values(self):
+        self._drop_svd()
+        oomega, iiomega = np.meshgrid(np.asarray(self.omega, dtype=np.float64), self.iomega)
+        self._K = 1.0 / (1.0j * iiomega - oomega)
+        self._K_delta = self._K * np.asarray(self.omega.delta)[None, :]      # trapezoid weights folded in
+        if self._T is not None:
+            raise NotImplementedError("a covariance rotation of complex Matsubara data is not on the fused path")
+
+    def fused_matrix(self):
+        return np.ascontiguousarray(np.vstack([self._K.real, self._K.imag]))
+
+    @staticmethod
+    def stack(x):
+        """[Re x; Im x] of a data-space vector (data, or an error bar repeated for both parts)."""
+        x = np.asarray(x)
+        return np.concatenate([x.real, x.imag]) if np.iscomplexobj(x) else np.concatenate([x, x])
+
+    def transform(self, T_):
+        if T_ is not None:
+            raise NotImplementedError("a covariance rotation of complex Matsubara data is not on the fused path")
+
+    @property
+    def data_variable(self):
+        return self.iomega
+
+    @data_variable.setter
+    def data_variable(self, value):
+        self.iomega = np.asarray(value, dtype=np.float64)
+        self._fill_values()
 
 
 class PreblurKernel(Kernel):

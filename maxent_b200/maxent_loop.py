@@ -91,6 +91,8 @@ class MaxEntLoop(object):
         variant = self.cost_function.variant() if variant is None else variant
         K = self.K
         err = np.asarray(self.err, dtype=np.float64) * np.ones(len(self.G))
+        if getattr(K, "is_complex", False):
+            err = K.stack(err)                               # the same error bar for real and imaginary part
         # the default model is NOT part of the key: jobs that differ only in D share the device problem and are
         # continued in one launch with one default model per spectrum (PoormanMaxEnt's off-diagonal pass)
         key = (id(K), K._svd_version, variant, _bytes(err), _bytes(self.omega.delta), _bytes(self.A_init),
@@ -99,7 +101,7 @@ class MaxEntLoop(object):
         if prob is None:
             while len(self._problem_cache) >= 4:
                 self._problem_cache.pop(next(iter(self._problem_cache)))
-            prob = engine.SharedProblem(K.K, err, self.D.D, self.omega.delta, variant=variant, device=self.device,
+            prob = engine.SharedProblem(K.fused_matrix(), err, self.D.D, self.omega.delta, variant=variant, device=self.device,
                                         A_init=self.A_init, usv=(K.U, K.S, K.V), orthonormal_U=K._T is None)
             prob.D_host = np.array(self.D.D, dtype=np.float64)
             self._problem_cache[key] = prob
@@ -109,7 +111,12 @@ class MaxEntLoop(object):
         """Freeze the current data set (G, error model, kernel, default model) as one *job* of the sweep.
         Several jobs that share their device problem are continued in ONE launch by ``run_jobs`` -- this is how
         ``ElementwiseMaxEnt`` batches matrix elements."""
-        G = np.array(self.G, dtype=np.float64)
+        cplx = getattr(self.K, "is_complex", False)
+        if np.iscomplexobj(self.G) and not cplx:
+            raise NotImplementedError("complex data need a complex kernel (IOmegaKernel); complex matrix elements of "
+                                      "G(tau) go through ElementwiseMaxEnt(use_complex=True)")
+        # complex Matsubara data enter the real fused path as the stacked rows [Re G; Im G] (kernels.IOmegaKernel)
+        G = self.K.stack(np.asarray(self.G)) if cplx else np.array(self.G, dtype=np.float64)
         job = dict(G=G, matrix_element=matrix_element, complex_index=complex_index, problem=None)
         if np.max(np.abs(G)) < self.G_threshold:
             return job                                       # skipped (python/maxent_loop.py:174-179)
@@ -122,8 +129,10 @@ class MaxEntLoop(object):
         blur = self.A_of_H._B if isinstance(self.A_of_H, PreblurA_of_H) else None     # A = B H (functions.py:991-993)
         job.update(problem=self.shared_problem(variant), scale=self._scale(), omega=self.omega, blur=blur,
                    D=np.array(self.D.D, dtype=np.float64),
-                   G_orig=np.array(self.cost_function.G_orig, dtype=np.float64),
+                   G_orig=np.array(self.cost_function.G_orig, dtype=complex if cplx else np.float64),
                    data_variable=np.array(self.data_variable, dtype=np.float64), K_delta=self.K.K_delta)
+        if cplx:
+            job["G_report"] = np.array(self.G, dtype=complex)
         return job
 
     def run_jobs(self, jobs, result=None):
@@ -181,7 +190,7 @@ class MaxEntLoop(object):
                 record = dict(alpha=alpha_eff, v=host["v"][b], chi2=host["chi2"][b], S=host["S"][b], Q=host["Q"][b],
                               A=A, H=H,
                               probability=host["logp"][b] if want_p else np.full(len(alpha_eff), np.nan),
-                              omega=job["omega"], G=job["G"], G_orig=job["G_orig"],
+                              omega=job["omega"], G=job.get("G_report", job["G"]), G_orig=job["G_orig"],
                               data_variable=job["data_variable"], G_rec=np.dot(A, np.asarray(job["K_delta"]).T),
                               n_iter=n_iter, converged=conv, n_sv=prob.n_sv)
                 run_time = result.end_timing(matrix_element=elem, complex_index=cidx)
@@ -205,7 +214,7 @@ class MaxEntLoop(object):
         """Run the alpha sweep for the current G and write it into ``result`` (a new ``MaxEntResult`` if None).
         Returns the result, or None when max|G| < G_threshold (the element is then listed in
         ``result.zero_elements``)."""
-        if np.max(np.abs(np.asarray(self.G, dtype=np.float64))) < self.G_threshold:
+        if np.max(np.abs(np.asarray(self.G))) < self.G_threshold:
             if result is not None and matrix_element is not None:
                 result.zero_elements.append(matrix_element)
             self.logtaker.error_message('G below threshold, not performing the calculation.')

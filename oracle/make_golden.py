@@ -158,6 +158,8 @@ def main():
     marquardt_case(m)
     mesh_case(m)
     covariance_case(m)
+    iomega_case(m)
+    config4_case(m)
 
 
 def preblur_case(m):
@@ -345,8 +347,58 @@ def config4_case(m):
     print("g13", out["ref_n_sv"], out["ref_wall"], {k: v for k, v in out.items() if k.startswith("ref_idx_")})
 
 
+def iomega_case(m):
+    """G14: continuation of Matsubara data G(i omega_n) with a REAL spectral function.  The reference's IOmegaKernel
+    (python/kernels.py:283-346) supplies the complex kernel; chi2 = sum |G - K H|^2 / sigma^2 (ComplexChi2.f,
+    python/functions.py:401-404) for a real H is NormalChi2 on the stacked rows [Re; Im], which the reference runs
+    through a DataKernel of that stacked matrix (MaxEntLoop driven as in test/python/maxent_loop.py:49-76)."""
+    beta, n_iw, n_omega, sigma = 40.0, 200, 100, 1.e-4
+    iomega = (2 * np.arange(n_iw) + 1) * np.pi / beta
+    omega = m.HyperbolicOmegaMesh(omega_min=-10, omega_max=10, n_points=n_omega)
+    K_iw = m.IOmegaKernel(iomega, omega, beta=beta)
+    A = np.exp(-(omega - 1.0)**2 / (2 * 0.5**2))
+    A /= np.trapz(A, omega)
+    rng = np.random.RandomState(4711)
+    G = np.dot(K_iw.K_delta, A) + sigma * (rng.randn(n_iw) + 1j * rng.randn(n_iw))
+    Ks = np.vstack([K_iw.K.real, K_iw.K.imag])
+    Gs = np.concatenate([G.real, G.imag])
+    errs = sigma * np.ones(2 * n_iw)
+    amesh = m.LogAlphaMesh(0.01, 2000, 20)
+
+    def run(Gin):
+        K = m.DataKernel(np.arange(2 * n_iw, dtype=float), omega, Ks)
+        D = m.FlatDefaultModel(omega=omega)
+        Q = m.MaxEntCostFunction(chi2=m.NormalChi2(K=K, G=Gin, err=errs), S=m.NormalEntropy(D=D), H_of_v=m.NormalH_of_v(D=D, K=K))
+        lt = m.Logtaker()
+        lt.verbose = m.VerbosityFlags.Quiet
+        ml = m.MaxEntLoop(cost_function=Q, alpha_mesh=amesh, logtaker=lt, reduce_singular_space=1e-11,
+                          scale_alpha=float(n_iw), probability="normal")
+        return K, ml.run()
+
+    K, res = run(Gs)
+    _, res2 = run(Gs * (1.0 + 1.e-15))
+    A1, A2 = np.array(res.A), np.array(res2.A)
+    out = dict(iomega=iomega, beta=beta, G=G, err=sigma, omega=np.array(omega), alpha_mesh=np.array(amesh), variant="normal",
+               use_probability=True, reduce_singular_space=1e-11, scale_alpha=float(n_iw),
+               ref_alpha=np.array(res.alpha), ref_chi2=np.array(res.chi2), ref_S=np.array(res.S), ref_Q=np.array(res.Q),
+               ref_A=A1, ref_H=np.array(res.H), ref_probability=np.array(res.probability, dtype=float), ref_n_sv=len(K.S),
+               ref_K_row0=np.array(K_iw.K)[0], ref_K_delta_row0=np.array(K_iw.K_delta)[0],
+               noise_A=np.max(np.abs(A1 - A2), axis=1) / np.max(np.abs(A1), axis=1),
+               noise_chi2=np.abs(np.array(res2.chi2) / np.array(res.chi2) - 1.0),
+               noise_S=np.abs(np.array(res2.S) / np.array(res.S) - 1.0))
+    for name, ar in res.analyzer_results.items():
+        if hasattr(ar, "keys") and "alpha_index" in ar:
+            out["ref_idx_" + name] = int(ar["alpha_index"])
+            if ar.get("A_out", None) is not None:
+                out["ref_Aout_" + name] = np.array(ar["A_out"])
+    np.savez_compressed(os.path.join(GOLD, "g14_iomega_200x100.npz"), **out)
+    print("g14", out["ref_n_sv"], {k: v for k, v in out.items() if k.startswith("ref_idx_")}, out["noise_A"].max())
+
+
 if __name__ == "__main__":
-    if "--elementwise-only" in sys.argv:
+    if "--iomega-only" in sys.argv:
+        iomega_case(import_reference())
+    elif "--elementwise-only" in sys.argv:
         elementwise_cases(import_reference())
     elif "--config4-only" in sys.argv:
         config4_case(import_reference())

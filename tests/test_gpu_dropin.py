@@ -482,6 +482,36 @@ def test_batched_threshold_skip_on_the_device():
     assert j2.prepare() is not p1 and j2.prepare().n_sv < p1.n_sv
 
 
+def test_iomega_kernel_matches_reference_run():
+    """G(i omega_n) -> real A(omega): IOmegaKernel + ComplexChi2 (python/kernels.py:283-346, python/functions.py:380-437)
+    through MaxEntLoop with complex data, against the run of the real reference on the stacked [Re; Im] system (g14):
+    200 Matsubara frequencies, 100 omega points, 20 alphas, probability.  Tiered contract, identical picks."""
+    g = gc.load_golden("g14_iomega_200x100.npz")
+    om = mb.DataOmegaMesh(g["omega"])
+    K = mb.IOmegaKernel(g["iomega"], om, beta=float(g["beta"]))
+    np.testing.assert_allclose(K.K[0], g["ref_K_row0"], rtol=1e-15)
+    np.testing.assert_allclose(K.K_delta[0], g["ref_K_delta_row0"], rtol=1e-15)
+    D = mb.FlatDefaultModel(omega=om)
+    G = g["G"]
+    assert np.iscomplexobj(G)
+    Q = mb.MaxEntCostFunction(chi2=mb.ComplexChi2(K=K, G=G, err=float(g["err"]) * np.ones(len(G))), S=mb.NormalEntropy(D=D),
+                              H_of_v=mb.NormalH_of_v(D=D, K=K))
+    ml = mb.MaxEntLoop(cost_function=Q, alpha_mesh=mb.DataAlphaMesh(g["alpha_mesh"]), reduce_singular_space=1e-11,
+                       scale_alpha=float(g["scale_alpha"]), probability='normal')
+    ml.set_verbosity(mb.VerbosityFlags.Quiet)
+    res = ml.run()
+    assert len(K.S) == int(g["ref_n_sv"]) and K.U.shape[0] == 2 * len(G) and not np.iscomplexobj(K.V)
+    gc.check_against_reference(g, _ResView(res))
+    # the reconstructed data are complex again: G_rec = K_delta A (python/maxent_result.py:905-908)
+    assert np.iscomplexobj(res.G_rec) and res.G_rec.shape == (20, len(G))
+    k = res.analyzer_results['LineFitAnalyzer']['alpha_index']
+    assert np.max(np.abs(res.G_rec[k] - G)) < 6 * float(g["err"])
+    # scale_alpha = 'Ndata' counts the complex data points (len(G), python/maxent_loop.py:216-220)
+    ml2 = mb.MaxEntLoop(cost_function=Q, alpha_mesh=mb.DataAlphaMesh(g["alpha_mesh"]), reduce_singular_space=1e-11)
+    ml2.set_verbosity(mb.VerbosityFlags.Quiet)
+    np.testing.assert_allclose(ml2.run().alpha, res.alpha, rtol=1e-15)
+
+
 def test_threshold_skip_and_unsupported_combinations():
     g = gc.load_golden("g2_synth_200x100.npz")
     tm = _tau_maxent_from_fixture(g)

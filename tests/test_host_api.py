@@ -98,9 +98,20 @@ def test_cost_function_variants():
                                                                                    H_of_v=mb.PlusMinusH_of_v())):
         with pytest.raises(NotImplementedError):
             bad.variant()
-    for cls in (mb.ComplexChi2, mb.NoExpH_of_v, mb.IOmegaKernel):
+    for cls in (mb.ComplexPlusMinusEntropy, mb.NoExpH_of_v, mb.ComplexPlusMinusH_of_v):
         with pytest.raises(NotImplementedError):
             cls()
+    # Matsubara kernel and complex misfit: host objects as in the reference (python/kernels.py:283-346), real A on the fused path
+    om_iw = mb.HyperbolicOmegaMesh(-5, 5, 30)
+    iw = (2 * np.arange(16) + 1) * np.pi / 10.0
+    Kiw = mb.IOmegaKernel(iw, om_iw, beta=10.0)
+    np.testing.assert_allclose(Kiw.K, 1.0 / (1j * iw[:, None] - np.asarray(om_iw)[None, :]), rtol=1e-15)
+    np.testing.assert_allclose(Kiw.K_delta, Kiw.K * om_iw.delta[None, :], rtol=1e-15)
+    assert Kiw.fused_matrix().shape == (32, 30) and np.all(Kiw.fused_matrix()[16:] == Kiw.K.imag)
+    np.testing.assert_array_equal(Kiw.stack(np.array([1 + 2j, 3 - 1j])), [1, 3, 2, -1])
+    assert mb.MaxEntCostFunction(chi2=mb.ComplexChi2(K=Kiw)).variant() == "normal"
+    with pytest.raises(NotImplementedError):
+        Kiw.transform(np.eye(16))
     om = mb.HyperbolicOmegaMesh(-5, 5, 40)
     pre = mb.PreblurA_of_H(b=0.3, omega=om)
     assert mb.MaxEntCostFunction(A_of_H=pre).variant() == "normal"
