@@ -25,7 +25,7 @@ from .analyzers import (Analyzer, AnalyzerResult, LineFitAnalyzer, Chi2Curvature
                         ClassicAnalyzer, BryanAnalyzer)
 from .maxent_result import MaxEntResult, MaxEntResultData, recursive_map, recursive_dtype, saved
 from .maxent_loop import MaxEntLoop
-from .preblur import get_preblur
+from .preblur import get_preblur, preblur_scan
 from .tau_maxent import TauMaxEnt
 from .elementwise_maxent import ElementwiseMaxEnt, DiagonalMaxEnt, PoormanMaxEnt, CallableMethodCheck
 from .batched import BatchedTauMaxEnt, BatchedMaxEntResult

@@ -78,7 +78,9 @@ __device__ double line_resid(const double* x, const double* y, int i0, int i1, i
     // least squares over indices [i0, i1) skipping NaN y; returns the residual sum of squares
     int n = 0; double mx = 0, my = 0;
     for (int i = i0; i < i1; ++i) if (!isnan(y[i])) { mx += x[i]; my += y[i]; ++n; }
-    if (n == 0) { *slope = nan(""); *icpt = nan(""); return 0.0; }
+    // np.polyfit raises TypeError on an empty piece and fit_piecewise then excludes this break point
+    // (linefit_analyzer.py:62-75): the residual is NaN, not 0
+    if (n == 0) { *slope = nan(""); *icpt = nan(""); return nan(""); }
     mx /= n; my /= n;
     double sxx = 0, sxy = 0, syy = 0;
     for (int i = i0; i < i1; ++i) if (!isnan(y[i])) { const double dx = x[i] - mx, dy = y[i] - my; sxx += dx * dx; sxy += dx * dy; syy += dy * dy; }

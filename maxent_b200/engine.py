@@ -284,6 +284,35 @@ def svd_jacobi_host(K, device=None):
         return U.cpu().numpy(), S.cpu().numpy(), V.cpu().numpy()
 
 
+class _PaddedView(object):
+    """A SharedProblem seen with a larger singular-space dimension: V' re-tiled with zero columns appended, xi and v0
+    zero-padded (see run_sweep, groups of different n_sv).  Everything else is the base problem's."""
+
+    def __init__(self, base, n_sv):
+        torch = _torch()
+        self.base = base
+        self.n_sv = int(n_sv)
+        pad = self.n_sv - base.n_sv
+        dev = base.device
+        z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            Vp = torch.cat([base.Vp, z(base.n_omega, pad)], dim=1).contiguous()
+            n = int(base.lib.mx_layout_V_size(base.n_omega, self.n_sv))
+            if n < 0:
+                raise _lib.MaxEntLibraryError("n_sv=%d outside the fused path (max %d)" % (self.n_sv, _lib.MX_MAX_NSV))
+            self.Vt = torch.empty(n, dtype=torch.float64, device=dev)
+            _lib.check(base.lib.mx_layout_V(_ptr(Vp), base.n_omega, self.n_sv, _ptr(self.Vt), _stream(dev)), "mx_layout_V")
+            self.xi = torch.cat([base.xi, z(pad)]).contiguous()
+            self.v0 = torch.cat([base.v0, z(pad)]).contiguous()
+            self.Vp = Vp
+
+    def __getattr__(self, name):                    # n_tau, n_omega, variant, D, delta, Qw, Q, sqrtw, lib, device, ...
+        return getattr(self.base, name)
+
+    def v_to_reference_basis(self, v):
+        return self.base.v_to_reference_basis(v[..., :self.base.n_sv])
+
+
 class SweepResult(object):
     """Device tensors produced by one call of the fused sweep (+ analyzers)."""
     __slots__ = ("alpha", "v", "A", "chi2", "S", "Q", "logp", "n_iter", "n_qeval", "n_solve", "status",
@@ -438,6 +467,13 @@ def run_sweep(prob, G, alpha_eff, probability=False, lm=None, chi2_factor=1.0, w
         B = int(G.shape[0])
         alpha = _dev_f64(np.asarray(alpha_eff, dtype=np.float64) if not torch.is_tensor(alpha_eff) else alpha_eff, dev)
         n_alpha, s, n_omega = int(alpha.numel()), prob.n_sv, prob.n_omega
+        if groups is not None and any(q.n_sv != s for q in groups[0]):
+            # groups with different singular-space dimensions (different kernels, e.g. the b values of a preblur scan):
+            # every group is padded with zero columns of V' (and zero xi, v0, g~) up to the largest.  The padded
+            # components never move (their rows of Z, J and f are exactly zero) and add exact zeros to every sum.
+            s = max(q.n_sv for q in groups[0])
+            prob = _PaddedView(prob, s)
+            groups = ([prob] + [_PaddedView(q, s) for q in groups[0][1:]], groups[1])
         rows = _Rows()
         ops = _ops()
         gt = torch.empty((B, s), dtype=f64, device=dev)
@@ -446,7 +482,7 @@ def run_sweep(prob, G, alpha_eff, probability=False, lm=None, chi2_factor=1.0, w
             probs, index = groups
             index = torch.as_tensor(np.asarray(index) if not torch.is_tensor(index) else index, device=dev).to(torch.int64)
             if probs[0] is not prob or any(q.n_sv != s or q.n_omega != n_omega or q.variant != prob.variant for q in probs):
-                raise ValueError("the problems of all groups must share kernel, cut and cost function")
+                raise ValueError("the problems of all groups must share the omega mesh and the cost function")
             if D is not None:
                 raise ValueError("per-spectrum default models and error groups cannot be combined yet")
             nvt = max(int(q.Vt.numel()) for q in probs)
@@ -466,10 +502,12 @@ def run_sweep(prob, G, alpha_eff, probability=False, lm=None, chi2_factor=1.0, w
                 if sel.numel() == 0:
                     continue
                 Gg = G[sel][:, :q.n_tau].contiguous()
-                gg = torch.empty((sel.numel(), s), dtype=f64, device=dev)
+                qq = getattr(q, "base", q)                 # projection in the group's own (unpadded) singular space
+                gg = torch.empty((sel.numel(), qq.n_sv), dtype=f64, device=dev)
                 cg = torch.empty((sel.numel(),), dtype=f64, device=dev)
-                ops.project_data(*_problem_args(q, alpha, False, lm, chi2_factor), Gg, gg, cg)
-                gt[sel] = gg
+                ops.project_data(*_problem_args(qq, alpha, False, lm, chi2_factor), Gg, gg, cg)
+                gt[sel] = 0.0
+                gt[sel, :qq.n_sv] = gg
                 c0[sel] = cg
         else:
             if G.shape[1] != prob.n_tau:

@@ -98,12 +98,15 @@ class MaxEntLoop(object):
         key = (id(K), K._svd_version, variant, _bytes(err), _bytes(self.omega.delta), _bytes(self.A_init),
                str(self.device))
         prob = self._problem_cache.get(key)
+        if prob is not None and prob.kernel_ref is not K:     # id() of a collected kernel can be reused by a new object
+            prob = None
         if prob is None:
             while len(self._problem_cache) >= 4:
                 self._problem_cache.pop(next(iter(self._problem_cache)))
             prob = engine.SharedProblem(K.fused_matrix(), err, self.D.D, self.omega.delta, variant=variant, device=self.device,
                                         A_init=self.A_init, usv=(K.U, K.S, K.V), orthonormal_U=K._T is None)
             prob.D_host = np.array(self.D.D, dtype=np.float64)
+            prob.kernel_ref = K                                # strong reference: the cache entry belongs to THIS kernel object
             self._problem_cache[key] = prob
         return prob
 
@@ -161,20 +164,49 @@ class MaxEntLoop(object):
                 groups[-1].append(job)
             else:
                 groups.append([job])
-        want_p = self.probability is not None
+        # Consecutive groups that differ only in their device problem (other kernel, other error model: e.g. the b values
+        # of a preblur scan, doc/guide/preblur_example.py:46-75) and use the problem's own default model go through ONE
+        # launch of the sweep as whitening groups (engine.run_sweep(groups=...)).
+        merged = []
         for group in groups:
+            p0 = group[0]["problem"]
+            own_D = all(np.array_equal(job["D"], job["problem"].D_host) for job in group)
+            last = merged[-1] if merged else None
+            if (last is not None and last["multi_ok"] and own_D and last["jobs"][0]["scale"] == group[0]["scale"]
+                    and last["jobs"][0]["problem"].variant == p0.variant and last["jobs"][0]["problem"].n_omega == p0.n_omega
+                    and last["jobs"][0]["problem"].n_tau == p0.n_tau
+                    and np.array_equal(last["jobs"][0]["problem"].D_host, p0.D_host)):
+                last["jobs"].extend(group)
+            else:
+                merged.append(dict(jobs=list(group), multi_ok=own_D))
+        want_p = self.probability is not None
+        for entry in merged:
+            group = entry["jobs"]
             prob, scale = group[0]["problem"], group[0]["scale"]
             alpha_eff = np.asarray(self.alpha_mesh, dtype=np.float64) * scale
             for job in group:
-                result.start_timing(matrix_element=job["matrix_element"], complex_index=job["complex_index"])
-            D_rows = np.stack([job["D"] for job in group])
-            if np.all(D_rows == prob.D_host[None, :]):
-                D_rows = None                                # the model the problem was built with: shared mode
-            res = engine.run_sweep(prob, np.stack([job["G"] for job in group]), alpha_eff, probability=want_p, lm=lm,
-                                   chi2_factor=self.cost_function.chi2_factor, want_A=True, want_v=True,
-                                   analyze_results=False, D=D_rows)
+                job.get("result", result).start_timing(matrix_element=job["matrix_element"], complex_index=job["complex_index"])
+            probs = []
+            for job in group:
+                if not any(job["problem"] is q for q in probs):
+                    probs.append(job["problem"])
+            Gs = np.stack([job["G"] for job in group])
+            if len(probs) > 1:
+                index = np.array([next(i for i, q in enumerate(probs) if q is job["problem"]) for job in group])
+                res = engine.run_sweep(prob, Gs, alpha_eff, probability=want_p, lm=lm,
+                                       chi2_factor=self.cost_function.chi2_factor, want_A=True, want_v=True,
+                                       analyze_results=False, groups=(probs, index))
+            else:
+                D_rows = np.stack([job["D"] for job in group])
+                if np.all(D_rows == prob.D_host[None, :]):
+                    D_rows = None                            # the model the problem was built with: shared mode
+                res = engine.run_sweep(prob, Gs, alpha_eff, probability=want_p, lm=lm,
+                                       chi2_factor=self.cost_function.chi2_factor, want_A=True, want_v=True,
+                                       analyze_results=False, D=D_rows)
             H_all = (res.A * prob.delta).cpu().numpy()          # the sweep writes H / delta (IdentityA_of_H)
-            host = dict(A=res.A.cpu().numpy(), v=prob.v_to_reference_basis(res.v).cpu().numpy(),
+            v_host = [job["problem"].v_to_reference_basis(res.v[b][..., :job["problem"].n_sv]).cpu().numpy()
+                      for b, job in enumerate(group)]
+            host = dict(A=res.A.cpu().numpy(), v=v_host,
                         chi2=res.chi2.cpu().numpy(), S=res.S.cpu().numpy(), Q=res.Q.cpu().numpy(),
                         logp=res.logp.cpu().numpy(), status=res.status.cpu().numpy(), n_iter=res.n_iter.cpu().numpy())
             width = str(int(np.ceil(np.log10(max(len(alpha_eff), 1)))))
@@ -192,8 +224,11 @@ class MaxEntLoop(object):
                               probability=host["logp"][b] if want_p else np.full(len(alpha_eff), np.nan),
                               omega=job["omega"], G=job.get("G_report", job["G"]), G_orig=job["G_orig"],
                               data_variable=job["data_variable"], G_rec=np.dot(A, np.asarray(job["K_delta"]).T),
-                              n_iter=n_iter, converged=conv, n_sv=prob.n_sv)
-                run_time = result.end_timing(matrix_element=elem, complex_index=cidx)
+                              n_iter=n_iter, converged=conv, n_sv=job["problem"].n_sv)
+                target = job.get("result", result)               # a job may bring its own result object (preblur_scan)
+                if target._default_analyzer_name is None:
+                    target._default_analyzer_name = result._default_analyzer_name
+                run_time = target.end_timing(matrix_element=elem, complex_index=cidx)
                 # the reference's per-alpha report (python/maxent_loop.py:248-255), printed from the device counters
                 for i, a in enumerate(alpha_eff):
                     self.logtaker.message(VerbosityFlags.AlphaLoop,
@@ -206,8 +241,8 @@ class MaxEntLoop(object):
                     self.logtaker.message(VerbosityFlags.AlphaLoop,
                                           "\n! ... The minimizer did not converge. Results might be wrong.\n")
                 self.logtaker.message(VerbosityFlags.Timing, "MaxEnt loop finished in {}", run_time)
-                result.add_sweep(record, matrix_element=elem, complex_index=cidx)
-                result.analyze(self.analyzers, matrix_element=elem, complex_index=cidx)
+                target.add_sweep(record, matrix_element=elem, complex_index=cidx)
+                target.analyze(self.analyzers, matrix_element=elem, complex_index=cidx)
         return result
 
     def run(self, result=None, matrix_element=None, complex_index=None):

@@ -512,6 +512,31 @@ def test_iomega_kernel_matches_reference_run():
     np.testing.assert_allclose(ml2.run().alpha, res.alpha, rtol=1e-15)
 
 
+def test_preblur_b_scan_in_one_launch():
+    """The b scan of the preblur workflow (doc/guide/preblur_example.py:46-75) as one batch: every b is a whitening group
+    of ONE launch of the sweep (its own kernel SVD, its own n_sv, V', xi).  Each b must reproduce the run of that b alone
+    (same bits: padding adds exact zeros), b = 0.3 the run of the real reference (fixture g7)."""
+    g = gc.load_golden("g7_preblur_200x100.npz")
+    tm = _tau_maxent_from_fixture(g)
+    K_tau = tm.K
+    bs = [0.1, 0.2, 0.3, 0.4]
+    scan = mb.preblur_scan(tm, bs)
+    assert sorted(scan) == bs and tm.K is K_tau
+    n_svs = []
+    for b in bs:
+        t1 = _tau_maxent_from_fixture(g)
+        K1 = t1.K
+        t1.A_of_H = mb.PreblurA_of_H(b=b, omega=t1.omega)
+        t1.K = mb.PreblurKernel(K=K1, b=b)
+        r1 = t1.run()
+        n_svs.append(len(t1.K.S))
+        np.testing.assert_array_equal(scan[b].chi2, r1.chi2)
+        np.testing.assert_array_equal(scan[b].A, r1.A)
+        assert scan[b].analyzer_results['LineFitAnalyzer']['alpha_index'] == r1.analyzer_results['LineFitAnalyzer']['alpha_index']
+    assert len(set(n_svs)) > 1, n_svs                      # the groups really had different singular-space dimensions
+    gc.check_against_reference(g, _ResView(scan[0.3]), rtol_chi2_S=2e-7)
+
+
 def test_threshold_skip_and_unsupported_combinations():
     g = gc.load_golden("g2_synth_200x100.npz")
     tm = _tau_maxent_from_fixture(g)

@@ -305,6 +305,16 @@ def test_analyzers_vs_oracle_on_mock_results(torch_cuda):
             else:
                 np.testing.assert_allclose(Aout[b, 4], br["A_out"], rtol=1e-12, atol=1e-14)
             np.testing.assert_array_equal(Aout[b, 0], A[b, idx[b, 0]])
+    # NaN chi2 at the first alphas (a failed / skipped solve): np.polyfit raises on an empty piece and fit_piecewise
+    # drops that break point (linefit_analyzer.py:62-75); the device must pick the same index as the oracle
+    chi2n = chi2.copy()
+    chi2n[0, :3] = np.nan
+    chi2n[3, -3:] = np.nan
+    chi2n[4, 5] = np.nan
+    idx, _ = engine.analyze(alpha, chi2n, S, logp, A)
+    idx = idx.cpu().numpy()
+    for b in range(B):
+        assert idx[b, 0] == mo.analyze_linefit(alpha, chi2n[b], A[b], 0)["alpha_index"], b
 
 
 def test_edge_cases(torch_cuda):
