@@ -213,6 +213,34 @@ class MaxEntResultData(object):
         return (self.alpha, np.exp(p - np.nanmax(p)),
                 self._matrix_opts(OrderedDict(label='$p$', x_label=r'$\alpha$', y_label='$p$', log_x=True, log_y=False)))
 
+    def plot_A(self, element=None, alpha_index=0, **kwargs):
+        """(omega, A_alpha(omega), options) of one alpha (python/maxent_result.py:468-501)."""
+        idx = slice(None) if element is None else element
+        return (self.omega, self.A[idx][alpha_index],
+                self._matrix_opts(OrderedDict(label=r'$A_{{\alpha_{}}}(\omega)$'.format(alpha_index), x_label=r'$\omega$',
+                                              y_label=r'$A(\omega)$', log_x=False, log_y=False,
+                                              n_alpha_index=len(self.alpha)), check_element_wise=False))
+
+    def plot_G(self, element=None, **kwargs):
+        """(data variable, original G, options) (python/maxent_result.py:503-539)."""
+        idx = slice(None) if element is None else element
+        return (self.data_variable[idx], self.G_orig[idx],
+                self._matrix_opts(OrderedDict(label=r'$G(d)$', x_label=r'$d$', y_label=r'$G(d)$', log_x=False, log_y=False),
+                                  check_element_wise=False))
+
+    def plot_G_rec(self, element=None, alpha_index=0, plot_G=True, **kwargs):
+        """List of curves: the original data (if ``plot_G``) and the reconstruction G_rec = K_delta A_alpha
+        (python/maxent_result.py:541-582)."""
+        ret = []
+        if plot_G:
+            ret.append(self.plot_G(element=element, **kwargs))
+        idx = slice(None) if element is None else element
+        ret.append((self.data_variable[idx], self.G_rec[idx][alpha_index],
+                    self._matrix_opts(OrderedDict(label=r'$G_{rec}(d)$', x_label=r'$d$', y_label=r'$G(d)$', log_x=False,
+                                                  log_y=False, plot_G=True, n_alpha_index=len(self.alpha)),
+                                      check_element_wise=False)))
+        return ret
+
     # ---- dict round trip (h5 / pickle; python/maxent_result.py:616-685) ---------------------------------
     def __reduce_to_dict__(self):
         out = dict(all_fields=self._all_fields)

@@ -274,6 +274,18 @@ def test_result_data_twin_and_pickle():
         r2.add_result(s, log_probability=None if i else -3.0)
     np.testing.assert_array_equal(r2.chi2, rec['chi2'][:3])
     assert r2.probability[0] == -3.0 and np.isnan(r2.probability[1])
+    # plot data providers (python/maxent_result.py:468-582): (x, y, options) tuples
+    x, y, opt = res.plot_A(alpha_index=2)
+    np.testing.assert_array_equal(x, res.omega)
+    np.testing.assert_array_equal(y, res.A[2])
+    assert opt['n_alpha_index'] == 5 and opt['x_label'] == r'$\omega$' and not opt['log_x']
+    x, y, opt = res.plot_G()
+    np.testing.assert_array_equal(x, res.data_variable)
+    np.testing.assert_array_equal(y, res.G_orig)
+    curves = res.plot_G_rec(alpha_index=1)
+    assert len(curves) == 2 and curves[1][2]['plot_G'] is True
+    np.testing.assert_array_equal(curves[1][1], res.G_rec[1])
+    assert len(res.plot_G_rec(alpha_index=1, plot_G=False)) == 1
 
 
 def test_no_cpu_fallback():
