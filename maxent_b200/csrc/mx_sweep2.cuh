@@ -478,12 +478,12 @@ template <int NT>
 struct Pipe {
     static constexpr int NSTAGE = Lay<NT>::NST;
     double* stage0;
-    const double* Vt;
     uint64_t* full;
     uint64_t* empty;
     int tid, lane, n_kt, nch;
 
-    __device__ __forceinline__ void issue(int c, unsigned g) const {      // thread 0 only
+    // Vt = the V' buffer of the spectrum in work (whitening groups bring their own, MxProblem.vt_index)
+    __device__ __forceinline__ void issue(int c, unsigned g, const double* __restrict__ Vt) const {      // thread 0 only
         const int st = g % NSTAGE;
         const int t0 = c * CH;
         const int nt = min(CH, n_kt - t0);
@@ -492,15 +492,15 @@ struct Pipe {
         bulk_g2s(stage0 + st * Lay<NT>::STAGE_D, Vt + (size_t)t0 * NT * 64, bytes, full + st);
     }
     // all threads; the staging area may have been used as scratch (generic proxy) since the last pass
-    __device__ __forceinline__ void begin(unsigned g0) const {
+    __device__ __forceinline__ void begin(unsigned g0, const double* __restrict__ Vt) const {
         __syncthreads();
         if (tid == 0) {
             fence_proxy_async();
-            for (int c = 0; c < NSTAGE - 1 && c < nch; ++c) issue(c, g0 + c);
+            for (int c = 0; c < NSTAGE - 1 && c < nch; ++c) issue(c, g0 + c, Vt);
         }
     }
     // wait for chunk c of the pass; thread 0 first tops the pipeline up (the stage of chunk c-1 is refilled)
-    __device__ __forceinline__ const double* wait(int c, unsigned g0, long long* pf = nullptr) const {
+    __device__ __forceinline__ const double* wait(int c, unsigned g0, const double* __restrict__ Vt, long long* pf = nullptr) const {
         const unsigned g = g0 + c;
 #ifdef MX_TPROF
         // diagnostics build: pf[0] time thread 0 waits for a free stage, pf[1] time it waits for data, pf[2] steps,
@@ -511,7 +511,7 @@ struct Pipe {
             if (cn < nch) {
                 if (c >= 1) mbar_wait(empty + (g - 1) % NSTAGE, ((g - 1) / NSTAGE) & 1);
                 pf[0] += clock64() - t0;
-                issue(cn, g0 + cn);
+                issue(cn, g0 + cn, Vt);
                 pf[8 + (g0 + cn) % NSTAGE] = clock64();
             }
             const long long w0 = clock64();
@@ -525,7 +525,7 @@ struct Pipe {
             const int cn = c + NSTAGE - 1;
             if (cn < nch) {
                 if (c >= 1) mbar_wait(empty + (g - 1) % NSTAGE, ((g - 1) / NSTAGE) & 1);
-                issue(cn, g0 + cn);
+                issue(cn, g0 + cn, Vt);
             }
         }
         __syncwarp();
@@ -543,7 +543,7 @@ struct Pipe {
 // k-group kg takes tiles 2 kg and 2 kg + 1), then the k-groups are added in a fixed order into Zfull (all NT x NT
 // tiles, C layout, symmetric fill).
 template <int NT, int TH>
-__device__ __forceinline__ void hpass_body(const Pipe<NT>& pipe, unsigned g0, const double* __restrict__ wrow, int kg,
+__device__ __forceinline__ void hpass_body(const Pipe<NT>& pipe, const double* __restrict__ Vt, unsigned g0, const double* __restrict__ wrow, int kg,
                                            int lane, int r, int q, int offY0, int offY1, double* __restrict__ Zf) {
     constexpr int NTRI = Lay<NT>::NTRI;
     const int n_kt = pipe.n_kt, nch = pipe.nch;
@@ -563,7 +563,7 @@ __device__ __forceinline__ void hpass_body(const Pipe<NT>& pipe, unsigned g0, co
     };
     double2 wa = loadw(2 * kg), wb = loadw(2 * kg + 1);
     for (int c = 0; c < nch; ++c) {
-        const double* stage = pipe.wait(c, g0);
+        const double* stage = pipe.wait(c, g0, Vt);
         const int kt = c * CH + 2 * kg;
         const double2 na = loadw(kt + CH), nb = loadw(kt + CH + 1);
         if (kt < n_kt) hpass_ktile<NT, TH>(stage + (2 * kg) * NT * 64, wa.x, wa.y, offY0, offY1, zacc);
@@ -621,7 +621,10 @@ __host__ __device__ constexpr int ctas_per_sm() {
     return n < 1 ? 1 : n;
 }
 
-template <int NT>
+// VAR = cost-function variant (MX_VARIANT_*), MARQ = Marquardt damping: compile-time, so that the code of the other
+// variants (the second pair of exponentials and the H rows of plus-minus, Bryan's scaling) costs the default path neither
+// registers nor instructions
+template <int NT, int VAR, bool MARQ>
 __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const SweepArgs a) {
     using LY = Lay<NT>;
     using LN = Lean<NT>;
@@ -635,8 +638,8 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
     const int r = lane >> 2, q = lane & 3;
     const int s = a.n_sv;
     const double eps_nu = a.nu * 2.220446049250313e-16;
-    const bool pm = a.variant == MX_VARIANT_PLUSMINUS;
-    const bool bryan = a.variant == MX_VARIANT_BRYAN;
+    constexpr bool pm = VAR == MX_VARIANT_PLUSMINUS;
+    constexpr bool bryan = VAR == MX_VARIANT_BRYAN;
     const int n_kt = a.n_kt;
     const int nch = (n_kt + CH - 1) / CH;
     const size_t rowlen = (size_t)n_kt * 8;
@@ -659,7 +662,8 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
     }
     __syncthreads();
 
-    Pipe<NT> pipe{sm + LY::o_stage, a.Vt, bar_full, bar_empty, tid, lane, n_kt, nch};
+    const Pipe<NT> pipe{sm + LY::o_stage, bar_full, bar_empty, tid, lane, n_kt, nch};
+    const double* Vsp = a.Vt;                  // V' of the spectrum in work
     const double* Dsp = a.D;
     // phase timers: thread 0 charges the cycles since the previous tick to phase k (only when the caller asked
     // for them: MxSweepOut.phase_cycles)
@@ -680,7 +684,7 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
     auto tpass = [&]() {
         const unsigned g0 = ctl.gchunk;
         const int nuniq = ctl.nuniq;
-        pipe.begin(g0);
+        pipe.begin(g0, Vsp);
         double tA[NT][2];
 #pragma unroll
         for (int jt = 0; jt < NT; ++jt) {
@@ -707,9 +711,9 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
         double2 Dv = loadD(warp);
         for (int c = 0; c < nch; ++c) {
 #ifdef MX_TPROF
-            const double* tile = pipe.wait(c, g0, timing ? ctl.pf : nullptr) + warp * NT * 64;
+            const double* tile = pipe.wait(c, g0, Vsp, timing ? ctl.pf : nullptr) + warp * NT * 64;
 #else
-            const double* tile = pipe.wait(c, g0) + warp * NT * 64;
+            const double* tile = pipe.wait(c, g0, Vsp) + warp * NT * 64;
 #endif
             const int kt = c * CH + warp;
             const bool valid = kt < n_kt;
@@ -813,12 +817,12 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
     // ---- H-pass: Z = V'^T diag(w) V' with w from scratch row `row` -> Zfull (all NT x NT tiles, C layout) ----
     auto hpass = [&](int row) {
         const unsigned g0 = ctl.gchunk;
-        pipe.begin(g0);
+        pipe.begin(g0, Vsp);
         const int kg = warp >> 1, th = warp & 1;
         const double* wrow = wscr + (size_t)row * rowlen;
         double* Zf = sm + LY::o_stage;
-        if (th == 0) hpass_body<NT, 0>(pipe, g0, wrow, kg, lane, r, q, offY0, offY1, Zf);
-        else hpass_body<NT, 1>(pipe, g0, wrow, kg, lane, r, q, offY0, offY1, Zf);
+        if (th == 0) hpass_body<NT, 0>(pipe, Vsp, g0, wrow, kg, lane, r, q, offY0, offY1, Zf);
+        else hpass_body<NT, 1>(pipe, Vsp, g0, wrow, kg, lane, r, q, offY0, offY1, Zf);
         if (tid == 0) ctl.gchunk = g0 + nch;
         __syncthreads();
     };
@@ -908,7 +912,7 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
             double m = INFINITY;
             for (int k = lane; k < s; k += 32) {
                 const double jd = fabs(sm[LY::o_jd + k]);
-                m = fmin(m, a.marquardt ? 1.0 : jd);
+                m = fmin(m, MARQ ? 1.0 : jd);
             }
             m = -warp_max(-m);
             if (lane == 0) ctl.jdmin = m;
@@ -918,7 +922,7 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
 
     // damping of diagonal entry i: mu * 1, or -- Marquardt's variant, levenberg_minimizer.py:181-185 -- mu * diag(J):
     // J_ii + mu * J_ii (for Bryan diag(eta Lambda Z) = diag(eta Xi Z Xi), so the symmetrised system carries the same shift)
-    const bool marq = a.marquardt != 0;
+    constexpr bool marq = MARQ;
     auto shift_of = [&](int i, double mu) -> double {
         return marq ? mu * sm[LY::o_jd + i] : mu;
     };
@@ -1004,7 +1008,7 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
         const int sp = ctl.spec;
         if (sp >= a.B) break;
         Dsp = a.D + (a.per_spec ? (size_t)sp * ((a.n_omega + 1) & ~1) : 0);       // per-spectrum default model (Poorman off-diagonals)
-        if (a.vt_index) pipe.Vt = a.Vt + (size_t)a.vt_index[sp] * (size_t)a.vt_stride;   // the V' of this spectrum's whitening group
+        if (a.vt_index) Vsp = a.Vt + (size_t)a.vt_index[sp] * (size_t)a.vt_stride;   // the V' of this spectrum's whitening group
         const double* const v0sp = a.v0 + (a.per_spec ? (size_t)sp * s : 0);
         for (int i = tid; i < SP; i += NTHR) {
             const double v0 = i < s ? v0sp[i] : 0.0;
@@ -1365,22 +1369,17 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
 // ------------------------------------------------------------------------------------------
 // host-side launch
 // ------------------------------------------------------------------------------------------
-template <int NT>
-int launch_sweep2(const SweepArgs& a, cudaStream_t stream, bool query, int* o_smem, int* o_grid) {
-    const size_t bytes = (size_t)Lay<NT>::total * sizeof(double);
-    if (o_smem) *o_smem = (int)bytes;
-    if (query && !o_grid) return MX_OK;                        // pure introspection: no device needed
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) { if (query) { *o_grid = 0; return MX_OK; } return MX_ERR_NO_DEVICE; }
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaFuncSetAttribute(sweep2_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+template <int NT, int VAR, bool MARQ>
+int launch_variant(const SweepArgs& a, cudaStream_t stream, bool query, size_t bytes, int sms, int* o_grid) {
+    auto kernel = sweep2_kernel<NT, VAR, MARQ>;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
         if (query) { cudaGetLastError(); if (o_grid) *o_grid = 0; return MX_OK; }
         return MX_ERR_CUDA;
     }
     // persistent CTAs: as many as are resident at once (registers and shared memory decide; ctas_per_sm<NT>() is what
     // the instantiation was compiled for)
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep2_kernel<NT>, NTHR, bytes) != cudaSuccess || per_sm < 1) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NTHR, bytes) != cudaSuccess || per_sm < 1) {
         cudaGetLastError();
         per_sm = 1;
     }
@@ -1393,8 +1392,30 @@ int launch_sweep2(const SweepArgs& a, cudaStream_t stream, bool query, int* o_sm
     if (grid < 1) grid = 1;
     if (o_grid) *o_grid = grid;
     if (query) return MX_OK;
-    sweep2_kernel<NT><<<grid, NTHR, bytes, stream>>>(a);
+    kernel<<<grid, NTHR, bytes, stream>>>(a);
     return cudaGetLastError() == cudaSuccess ? MX_OK : MX_ERR_CUDA;
+}
+
+template <int NT>
+int launch_sweep2(const SweepArgs& a, cudaStream_t stream, bool query, int* o_smem, int* o_grid) {
+    const size_t bytes = (size_t)Lay<NT>::total * sizeof(double);
+    if (o_smem) *o_smem = (int)bytes;
+    if (query && !o_grid) return MX_OK;                        // pure introspection: no device needed
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { if (query) { *o_grid = 0; return MX_OK; } return MX_ERR_NO_DEVICE; }
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (a.marquardt) {
+        switch (a.variant) {
+            case MX_VARIANT_NORMAL: return launch_variant<NT, MX_VARIANT_NORMAL, true>(a, stream, query, bytes, sms, o_grid);
+            case MX_VARIANT_PLUSMINUS: return launch_variant<NT, MX_VARIANT_PLUSMINUS, true>(a, stream, query, bytes, sms, o_grid);
+            default: return launch_variant<NT, MX_VARIANT_BRYAN, true>(a, stream, query, bytes, sms, o_grid);
+        }
+    }
+    switch (a.variant) {
+        case MX_VARIANT_NORMAL: return launch_variant<NT, MX_VARIANT_NORMAL, false>(a, stream, query, bytes, sms, o_grid);
+        case MX_VARIANT_PLUSMINUS: return launch_variant<NT, MX_VARIANT_PLUSMINUS, false>(a, stream, query, bytes, sms, o_grid);
+        default: return launch_variant<NT, MX_VARIANT_BRYAN, false>(a, stream, query, bytes, sms, o_grid);
+    }
 }
 
 constexpr int threads_per_cta() { return NTHR; }

@@ -23,7 +23,8 @@ def child(lib, spectra, phases, out_npz, cost_function):
     import numpy as np
     import torch
     from maxent_b200 import batched, engine
-    job = batched.BatchedTauMaxEnt(reduce_singular_space=1e-11, cost_function=cost_function)
+    job = batched.BatchedTauMaxEnt(reduce_singular_space=1e-11, cost_function=cost_function,
+                                   svd=os.environ.get("MX_AB_SVD", "jacobi"))
     G = batched.synthetic_bootstrap_batch(2000, 1000, spectra, seed=5)
     job.set_kernel_tau(np.linspace(0.0, 40.0, 2000), batched.hyperbolic_omega(-10.0, 10.0, 1000), beta=40.0)
     job.set_alpha_mesh_log(0.01, 2000.0, 60)
