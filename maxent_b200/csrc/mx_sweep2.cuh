@@ -324,8 +324,7 @@ __device__ __forceinline__ double2 lean_tile(const double* __restrict__ Lsm, con
 template <int NT, int JB, bool FWD, class Load>
 __device__ __forceinline__ void lean_steps(Load& load, double* __restrict__ Lsm, double (&R)[Lean<NT>::RDIM][2], double (&U)[NT][2],
                                            bool& ok, double& logdet, bool want_logdet, int r, int q, int lane,
-                                           const double* __restrict__ rhs, double (&zc)[NT][2], double* __restrict__ zscr,
-                                           double* __restrict__ dinv) {
+                                           const double* __restrict__ rhs, double* __restrict__ zscr, double* __restrict__ dinv) {
     if constexpr (JB < NT) {
         constexpr int NC = NT - JB;
         double C[NC][2];
@@ -389,19 +388,19 @@ __device__ __forceinline__ void lean_steps(Load& load, double* __restrict__ Lsm,
         if constexpr (FWD) {
             double acc = 0.0;
 #pragma unroll
-            for (int J = 0; J < JB; ++J) {
+            for (int J = 0; J < JB; ++J) {              // w_J = D^-1 z_J of the finished blocks comes back from shared memory
                 const double2 t = lean_tile<NT>(Lsm, R, JB, J, lane);
-                acc = fma(t.x, zc[J][0], fma(t.y, zc[J][1], acc));
+                const double2 wJ = *reinterpret_cast<const double2*>(zscr + 8 * J + 2 * q);
+                acc = fma(t.x, wJ.x, fma(t.y, wJ.y, acc));
             }
             double rr = rhs[8 * JB + r];
             if (JB > 0) rr -= quadreduce(acc);
             const double z0 = colreduce(U[JB][0] * rr), z1 = colreduce(U[JB][1] * rr);       // z = L^-1 rhs (unit L)
-            if (r == 0) *reinterpret_cast<double2*>(zscr + 8 * JB + 2 * q) = make_double2(z0, z1);
             const double2 dj = *reinterpret_cast<const double2*>(dinv + 8 * JB + 2 * q);
-            zc[JB][0] = z0 * dj.x;                                                           // D^-1 z feeds the next blocks
-            zc[JB][1] = z1 * dj.y;
+            if (r == 0) *reinterpret_cast<double2*>(zscr + 8 * JB + 2 * q) = make_double2(z0 * dj.x, z1 * dj.y);
+            __syncwarp();
         }
-        lean_steps<NT, JB + 1, FWD>(load, Lsm, R, U, ok, logdet, want_logdet, r, q, lane, rhs, zc, zscr, dinv);
+        lean_steps<NT, JB + 1, FWD>(load, Lsm, R, U, ok, logdet, want_logdet, r, q, lane, rhs, zscr, dinv);
     }
 }
 
@@ -421,11 +420,12 @@ __device__ __forceinline__ void lean_solve(const double* __restrict__ Lsm, const
             c0 = fma(t.x, xr[I], c0);
             c1 = fma(t.y, xr[I], c1);
         }
-        const double2 z = *reinterpret_cast<const double2*>(zscr + 8 * jb + 2 * q);
-        double z0 = z.x, z1 = z.y;
-        if (jb < NT - 1) { z0 -= colreduce(c0); z1 -= colreduce(c1); }
-        const double2 dj = *reinterpret_cast<const double2*>(dinv + 8 * jb + 2 * q);
-        z0 *= dj.x; z1 *= dj.y;
+        const double2 w = *reinterpret_cast<const double2*>(zscr + 8 * jb + 2 * q);      // D^-1 L^-1 rhs
+        double z0 = w.x, z1 = w.y;
+        if (jb < NT - 1) {
+            const double2 dj = *reinterpret_cast<const double2*>(dinv + 8 * jb + 2 * q);
+            z0 = fma(-dj.x, colreduce(c0), z0); z1 = fma(-dj.y, colreduce(c1), z1);
+        }
         xr[jb] = quadreduce(fma(U[jb][0], z0, U[jb][1] * z1));
     }
     __syncwarp();
@@ -952,10 +952,9 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
             double U[NT][2];
             bool ok = true;
             double ld = 0.0;
-            double zc[NT][2];
             double* const trow = sm + LY::o_tb + u * SP;          // scratch for the forward substitution, then t = v - dv
             double* const dinv = sm + LY::o_yb + u * SP;          // 1 / d of the L D L^T factorisation (yb is dead here)
-            lean_steps<NT, 0, true>(load, Lsm, R, U, ok, ld, false, r, q, lane, sm + LY::o_rhs, zc, trow, dinv);
+            lean_steps<NT, 0, true>(load, Lsm, R, U, ok, ld, false, r, q, lane, sm + LY::o_rhs, trow, dinv);
             ok = __all_sync(0xffffffffu, ok);
             double xr[NT];
             lean_solve<NT>(Lsm, R, U, dinv, xr, r, q, lane, trow);
@@ -992,8 +991,7 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
         double ld = 0.0;
         double* const Lsm = sm + LY::o_J;                  // J of the finished iteration is dead: park the tiles there
         double R[LN::RDIM][2];
-        double zc[NT][2];
-        lean_steps<NT, 0, false>(entry, Lsm, R, U, ok, ld, true, r, q, lane, nullptr, zc, nullptr, sm + LY::o_yb);
+        lean_steps<NT, 0, false>(entry, Lsm, R, U, ok, ld, true, r, q, lane, nullptr, nullptr, sm + LY::o_yb);
         ok = __all_sync(0xffffffffu, ok);
         return ok ? ld : nan("");
     };
