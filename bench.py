@@ -210,12 +210,19 @@ def run_native(a):
     # ---- the job: one BatchedTauMaxEnt per rank over its shard of the bootstrap batch ------------
     B = a.spectra
     job = batched.BatchedTauMaxEnt(cost_function=a.cost_function, reduce_singular_space=a.thr, device=dev)
-    t0 = time.time()
     G_host = batched.synthetic_bootstrap_batch(a.n_tau, a.n_omega, B, first=rank * B, seed=5, pin=True)
     job.set_kernel_tau(np.linspace(0.0, 40.0, a.n_tau), batched.hyperbolic_omega(-10.0, 10.0, a.n_omega), beta=40.0)
     job.set_alpha_mesh_log(0.01, 2000.0, a.n_alpha)
     job.set_error(1.e-4)
-    job.prepare()                                   # kernel fill, Jacobi SVD, truncation, V' layout (once per kernel)
+    torch.zeros(1, device=dev)                      # CUDA context and library load are not kernel set-up
+    torch.cuda.synchronize()
+    t0 = time.time()
+    job.prepare()                                   # kernel fill, truncated SVD, truncation, V' layout (once per kernel)
+    torch.cuda.synchronize()
+    setup_first_s = time.time() - t0                # includes the first-use costs of the library (module load, allocator)
+    job.problem = None
+    t0 = time.time()
+    job.prepare()
     torch.cuda.synchronize()
     setup_s = time.time() - t0
     prob = job.problem
@@ -234,8 +241,15 @@ def run_native(a):
         ps = ClockSampler(local)
         ps.start()
         t_dmma, t_dfma = ctypes.c_double(0.0), ctypes.c_double(0.0)
-        rc = lib.mx_fp64_peak(ctypes.byref(t_dmma), ctypes.byref(t_dfma), ctypes.c_void_p(scratch.data_ptr()),
-                              ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        t_pk = time.time()
+        best = [0.0, 0.0]
+        while True:                                 # ~1.5 s, so that the clock sampler sees the pipe under this load
+            rc = lib.mx_fp64_peak(ctypes.byref(t_dmma), ctypes.byref(t_dfma), ctypes.c_void_p(scratch.data_ptr()),
+                                  ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            best = [max(best[0], t_dmma.value), max(best[1], t_dfma.value)]
+            if rc != 0 or time.time() - t_pk > 1.5:
+                break
+        t_dmma.value, t_dfma.value = best
         pc = ps.stop()
         if rc == 0 and t_dmma.value > 1.0:
             peak_meas = {"dmma_tflops": t_dmma.value, "dfma_tflops": t_dfma.value, "sm_mhz": pc.get("sm_mhz"),
@@ -348,7 +362,8 @@ def run_native(a):
                        "final_gather_ms_once_per_job": round(gather_ms, 3), "G_sha256_first_64_rows": g_sha,
                        "optional_full_A_alpha_d2h": {"bytes_per_step": full_A_bytes, "ms_per_step_extrapolated": round(full_A_ms, 1),
                                                      "note": "not part of e2e: A_alpha stays on the device, e2e returns A_out of the five analyzers"},
-                       "setup_s_once_per_kernel": round(setup_s, 3), "svd_sweeps": getattr(prob, "svd_sweeps", None),
+                       "setup_s_once_per_kernel": round(setup_s, 3), "setup_s_first_call": round(setup_first_s, 3),
+                       "svd": getattr(prob, "svd_sweeps", None),
                        "spectra_per_cta": prob.config["spectra_per_cta"], "smem_bytes": prob.config["smem_bytes"],
                        "lm_iterations_per_spectrum": n_iter / B, "q_evals_per_spectrum": n_q / B, "solves_per_spectrum": n_s / B,
                        "device_trials_per_lm_iteration": n_trial / max(n_iter, 1),
