@@ -25,7 +25,8 @@ extern "C" {
 #define MX_ERR_CUDA         -3
 #define MX_ERR_NO_DEVICE    -4
 
-#define MX_MAX_NSV          80   /* singular-space dimension the fused path supports */
+#define MX_MAX_NSV         256   /* singular-space dimension the fused path supports: up to 80 with every matrix in
+                                    * shared memory and registers, 81..256 with Z, J and the factors in the workspace */
 
 /* sweep engines (MxProblem.engine) */
 #define MX_ENGINE_AUTO       0   /* = MX_ENGINE_SPECTRUM_CTA */
@@ -164,6 +165,12 @@ int mx_svd_jacobi(const double* K, int32_t m, int32_t n, double* U, double* S, d
 int64_t mx_svd_truncated_work_doubles(int32_t m, int32_t n, int32_t p);
 int mx_svd_truncated(const double* K, int32_t m, int32_t n, int32_t p, double* U, double* S, double* V,
                      double* work, uint64_t seed, void* stream);
+
+/* Orthonormalise the p rows of Yt[p, len] in place, in order (classical Gram-Schmidt, every row projected three times
+ * against the finished ones, one CTA; p <= 512).  A row whose residual falls below drop_rel times its norm is zeroed
+ * (drop_rel = 0: never).  Used for Q = the left vectors of the whitened kernel, whose orthogonality chi2 relies on
+ * (python/functions.py:358-360 evaluates chi2 with the full kernel and needs no such step). */
+int mx_gram_schmidt_rows(double* Yt, int32_t len, int32_t p, double drop_rel, void* stream);
 
 /* Project the data of B spectra into the singular space:
  *   gt[b] = Qw^T G[b]  and  c0[b] = | sqrtw*G[b] - Qo gt[b] |^2

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MAXENT_B200_LIB") or os.path.join(HERE, "libmaxent_b200.so")
 
 MX_OK = 0
-MX_MAX_NSV = 80
+MX_MAX_NSV = 256
 ENGINE_AUTO, ENGINE_LOCKSTEP, ENGINE_SPECTRUM_CTA = 0, 1, 2
 VARIANTS = {"normal": 0, "plusminus": 1, "bryan": 2}
 AN_LINEFIT, AN_CHI2CURV, AN_ENTROPY, AN_CLASSIC, AN_BRYAN = range(5)
@@ -61,6 +61,7 @@ SYMBOLS = [
     ("mx_tau_kernel", ctypes.c_int, [c_dp, c_dp, ctypes.c_int32, ctypes.c_int32, ctypes.c_double, c_dp, c_dp]),
     ("mx_svd_jacobi", ctypes.c_int, [c_dp, ctypes.c_int32, ctypes.c_int32, c_dp, c_dp, c_dp, c_dp,
                                      ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), c_dp]),
+    ("mx_gram_schmidt_rows", ctypes.c_int, [c_dp, ctypes.c_int32, ctypes.c_int32, ctypes.c_double, ctypes.c_void_p]),
     ("mx_svd_truncated_work_doubles", ctypes.c_int64, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]),
     ("mx_svd_truncated", ctypes.c_int, [c_dp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_dp, c_dp, c_dp, c_dp,
                                         ctypes.c_uint64, c_dp]),

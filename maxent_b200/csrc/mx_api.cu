@@ -274,16 +274,13 @@ int mx_device_sm_count(void) {
 int64_t mx_layout_V_size(int32_t n_omega, int32_t n_sv) {
     if (n_omega < 1 || n_sv < 1 || n_sv > MX_MAX_NSV) return MX_ERR_BAD_ARG;
     const int64_t n_kt = (n_omega + 7) / 8;
-    int nt = (n_sv + 7) / 8;
-    if (nt < 4) nt = 4;
-    return n_kt * nt * 64;
+    return n_kt * sweep_tiles(n_sv) * 64;
 }
 
 int mx_layout_V(const double* V, int32_t n_omega, int32_t n_sv, double* Vt, void* stream) {
     const int64_t total = mx_layout_V_size(n_omega, n_sv);
     if (total < 0 || !V || !Vt) return MX_ERR_BAD_ARG;
-    int nt = (n_sv + 7) / 8;
-    if (nt < 4) nt = 4;
+    const int nt = sweep_tiles(n_sv);
     const int grid = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
     layout_V_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(V, n_omega, n_sv, nt, Vt, total);
     return cudaGetLastError() == cudaSuccess ? MX_OK : MX_ERR_CUDA;
@@ -333,6 +330,11 @@ int mx_fp64_peak(double* tflops_dmma, double* tflops_dfma, double* scratch, void
     *tflops_dmma = best[0];
     *tflops_dfma = best[1];
     return cudaGetLastError() == cudaSuccess ? MX_OK : MX_ERR_CUDA;
+}
+
+int mx_gram_schmidt_rows(double* Yt, int32_t len, int32_t p, double drop_rel, void* stream) {
+    if (!Yt || len < 1 || p < 1 || p > 512) return MX_ERR_BAD_ARG;
+    return mx::gram_schmidt_rows(Yt, len, p, drop_rel, (cudaStream_t)stream);
 }
 
 int64_t mx_svd_truncated_work_doubles(int32_t m, int32_t n, int32_t p) {
@@ -392,8 +394,8 @@ int mx_sweep_config(int32_t n_sv, int32_t engine, int32_t* engine_used, int32_t*
 
 static const int64_t WS_HEADER = 256;     // bytes reserved for the work counter in front of the scratch rows
 
-int64_t mx_sweep_workspace_bytes(const MxProblem* p, int32_t B) {
-    if (!p || B < 0) return MX_ERR_BAD_ARG;
+// persistent CTAs the sweep would be launched with (what the workspace is sized for)
+static int sweep_grid(const MxProblem* p, int32_t B, int* grid) {
     SweepArgs a = {};
     a.n_sv = p->n_sv;
     a.B = B > 0 ? B : 1;
@@ -401,11 +403,20 @@ int64_t mx_sweep_workspace_bytes(const MxProblem* p, int32_t B) {
     a.per_spec_xi = (p->per_spectrum_model & MX_PER_SPECTRUM_XI) ? 1 : 0;
     a.per_spec_alpha = (p->per_spectrum_model & MX_PER_SPECTRUM_ALPHA) ? 1 : 0;
     a.marquardt = p->lm.marquardt ? 1 : 0;
+    a.variant = p->variant;
     a.conv_absq = p->lm.conv_abs_change;
-    int eng = 0, grid = 0;
-    const int rc = dispatch_sweep(a, nullptr, true, p->engine, &eng, nullptr, nullptr, &grid);
+    int eng = 0;
+    *grid = 0;
+    const int rc = dispatch_sweep(a, nullptr, true, p->engine, &eng, nullptr, nullptr, grid);
     if (rc != MX_OK) return rc;
-    if (grid <= 0) return MX_ERR_NO_DEVICE;
+    return *grid > 0 ? MX_OK : MX_ERR_NO_DEVICE;
+}
+
+int64_t mx_sweep_workspace_bytes(const MxProblem* p, int32_t B) {
+    if (!p || B < 0) return MX_ERR_BAD_ARG;
+    int grid = 0;
+    const int rc = sweep_grid(p, B, &grid);
+    if (rc != MX_OK) return rc;
     return WS_HEADER + 8 * sweep_scratch_doubles(p->n_sv, p->n_omega, p->variant, grid);
 }
 
@@ -417,8 +428,10 @@ int mx_alpha_sweep(const MxProblem* p, const double* gt, const double* c0, int32
     SweepArgs a = {};
     int rc = fill_args(p, a);
     if (rc != MX_OK) return rc;
-    const int64_t need = mx_sweep_workspace_bytes(p, B);
-    if (need < 0) return (int)need;
+    int grid = 0;
+    rc = sweep_grid(p, B, &grid);
+    if (rc != MX_OK) return rc;
+    const int64_t need = WS_HEADER + 8 * sweep_scratch_doubles(p->n_sv, p->n_omega, p->variant, grid);
     if (workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return MX_ERR_BAD_ARG;
     a.B = B; a.gt = gt; a.c0 = c0;
     a.o_v = out->v; a.o_A = out->A; a.o_chi2 = out->chi2; a.o_S = out->S; a.o_Q = out->Q; a.o_logp = out->logp;
@@ -426,6 +439,8 @@ int mx_alpha_sweep(const MxProblem* p, const double* gt, const double* c0, int32
     a.o_ntrial = out->n_trial; a.o_nbatch = out->n_batch; a.o_phase = reinterpret_cast<long long*>(out->phase_cycles);
     a.counter = reinterpret_cast<int*>(workspace);
     a.scratch = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + WS_HEADER);
+    a.wide_stride = sweep_wide_stride(p->n_sv);         // the slices of the wide instantiations follow the scratch rows
+    a.wide = a.wide_stride ? a.scratch + sweep_rows_doubles(p->n_omega, p->variant, grid) : nullptr;
     if (cudaMemsetAsync(workspace, 0, WS_HEADER, (cudaStream_t)stream) != cudaSuccess) return MX_ERR_CUDA;
     return dispatch_sweep(a, (cudaStream_t)stream, false, p->engine, nullptr, nullptr, nullptr, nullptr);
 }

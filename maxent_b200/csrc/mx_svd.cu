@@ -236,6 +236,11 @@ __global__ void __launch_bounds__(1024) cgs_kernel(double* __restrict__ Yt, int 
     }
 }
 
+int gram_schmidt_rows(double* Yt, int len, int p, double drop_rel, cudaStream_t stream) {
+    cgs_kernel<<<1, 1024, 0, stream>>>(Yt, len, p, drop_rel);
+    return cudaGetLastError() == cudaSuccess ? MX_OK : MX_ERR_CUDA;
+}
+
 __global__ void __launch_bounds__(256) col_norm_kernel(const double* __restrict__ At, int len, int p, double* __restrict__ S) {
     __shared__ double red[8];
     const int j = blockIdx.x;

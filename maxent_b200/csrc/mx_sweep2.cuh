@@ -187,15 +187,26 @@ __host__ __device__ constexpr int stage_count(int NT) {
 // ------------------------------------------------------------------------------------------
 // shared-memory layout (offsets in doubles)
 // ------------------------------------------------------------------------------------------
+// Wide singular spaces (NT > 10 tiles, n_sv up to 256): Z, J and the factors of the trial systems do not fit in shared
+// memory any more.  They live in a per-CTA slice of the global workspace (L2-resident), V' is read straight from L2
+// (no staging ring), one CTA per SM with the full register file; everything else -- the replay of the damping search,
+// the pointwise map, the order of every sum inside a spectrum -- is the code of the narrow instantiations.
+__host__ __device__ constexpr bool is_wide(int NT) { return NT > 10; }
+__host__ __device__ constexpr long long wide_doubles(int NT) {     // Zfull + J + one factor per warp (diagonal slots = U tiles)
+    return is_wide(NT) ? (long long)(NT * NT + (1 + NWARP) * (NT * (NT + 1) / 2)) * 64 : 0;
+}
+
 template <int NT>
 struct Lay {
+    static constexpr bool WIDE = is_wide(NT);
     static constexpr int SP = 8 * NT;
     static constexpr int NTRI = NT * (NT + 1) / 2;
     static constexpr int STAGE_D = CH * NT * 64;
-    static constexpr int NST = stage_count(NT);
+    static constexpr int NST = WIDE ? 0 : stage_count(NT);
+    static constexpr int STAGE_AREA = WIDE ? NWARP * 8 * SP : NST * STAGE_D;   // wide: only the y partials of the T-pass
     static constexpr int o_stage = 0;                              // NST x STAGE_D ; aliases: Zfull [NT*NT*64], yred [NWARP][8][SP], parked Cholesky tiles
-    static constexpr int o_J = o_stage + NST * STAGE_D;         // NTRI tiles, C layout (also: partial Z tiles of the H-pass, parked tiles of the log-det)
-    static constexpr int o_tb = o_J + NTRI * 64;                   // [8][SP] trial vectors t_b = v - dv_b  (the accepted one IS the new v, levenberg_minimizer.py:239)
+    static constexpr int o_J = o_stage + STAGE_AREA;            // NTRI tiles, C layout (also: partial Z tiles of the H-pass, parked tiles of the log-det)
+    static constexpr int o_tb = o_J + (WIDE ? 0 : NTRI * 64);      // [8][SP] trial vectors t_b = v - dv_b  (the accepted one IS the new v, levenberg_minimizer.py:239)
     static constexpr int o_yb = o_tb + MAXB * SP;                  // [8][SP]
     static constexpr int o_ctb = o_yb + MAXB * SP;                 // carried candidate: t, y
     static constexpr int o_cy = o_ctb + SP;
@@ -212,11 +223,11 @@ struct Lay {
     static constexpr int o_ctl = o_sred + NWARP * 8;                      // Ctl block (192 doubles reserved)
     static constexpr int o_bar = o_ctl + 192;                      // 2*NST mbarriers
     static constexpr int total = o_bar + 2 * NST;
-    static_assert(NT * NT * 64 <= NST * STAGE_D, "Zfull must fit in the staging area");
-    static_assert(NWARP * 8 * SP <= NST * STAGE_D, "yred must fit in the staging area");
-    static_assert(solver_warps(NT) * Lean<NT>::NSMT * 64 <= NST * STAGE_D, "the parked tiles of the solver warps must fit in the staging area");
-    static_assert(Lean<NT>::NSMT <= NTRI, "the parked tiles of the log-det factorisation must fit in the J area");
-    static_assert(NT * NT * 64 + (NKG - 1) * NTRI * 64 <= o_ctb, "partial Z tiles of the H-pass must fit behind Zfull");
+    static_assert(WIDE || NT * NT * 64 <= NST * STAGE_D, "Zfull must fit in the staging area");
+    static_assert(NWARP * 8 * SP <= STAGE_AREA, "yred must fit in the staging area");
+    static_assert(WIDE || solver_warps(NT) * Lean<NT>::NSMT * 64 <= NST * STAGE_D, "the parked tiles of the solver warps must fit in the staging area");
+    static_assert(WIDE || Lean<NT>::NSMT <= NTRI, "the parked tiles of the log-det factorisation must fit in the J area");
+    static_assert(WIDE || NT * NT * 64 + (NKG - 1) * NTRI * 64 <= o_ctb, "partial Z tiles of the H-pass must fit behind Zfull");
 };
 
 enum { PH_FIRST = 0, PH_PUMP, PH_PROBE, PH_WALK, PH_DONE };
@@ -298,6 +309,217 @@ __device__ bool lm_run(LM& s, double nu, double max_mu, double eps_nu, Look&& lo
             default: return true;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// Replay of the damping search on the tabulated trials and, when a value is missing, the plan of the next batch.
+// Run by ONE warp (all 32 lanes, warp-uniform); everything it decides goes through the control block.
+// jdv = diagonal of J, tb / yb = trial vectors and their y of the last batch ([8][SP]), ctb / cy = the carried candidate.
+// Sets ctl.conv = 1 when the iteration's search is decided, otherwise ctl.nuniq / umu / bmu describe the next batch.
+// ------------------------------------------------------------------------------------------
+template <bool MARQ, class Tick>
+__device__ __forceinline__ void replay_and_plan(Ctl& ctl, const SweepArgs& a, double eps_nu, int s, int SP, int lane,
+                                                const double* __restrict__ jdv, const double* __restrict__ tb,
+                                                const double* __restrict__ yb, double* __restrict__ ctb,
+                                                double* __restrict__ cy, bool timing, Tick&& tick) {
+    (void)timing;
+    auto shift_of = [&](int i, double mu) -> double { return MARQ ? mu * jdv[i] : mu; };
+    // The whole warp runs the (scalar, warp-uniform) state machine.  The tables live in registers:
+    // lane i holds table entry i (damping, unique trial) and unique trial i (damping, Q, failed);
+    // searches are ballots, reads are shuffles.
+    LM L = ctl.lm;
+    int ns = ctl.ns, nq = ctl.nq;
+    
+    const double jdmin = ctl.jdmin;
+    const int nb0 = ctl.nb, nu0 = ctl.nuniq;
+    int carry_row = ctl.urow[ID_CARRY];
+    double t_mu = lane < nb0 ? ctl.bmu[lane] : 0.0;
+    int t_slot = lane < nb0 ? ctl.bslot[lane] : 0;
+    const bool uvalid = lane < nu0 || (lane == ID_CARRY && carry_row >= 0);
+    double u_mu = uvalid ? ctl.umu[lane] : 0.0;
+    double u_Q = uvalid ? ctl.uQ[lane] : 0.0;
+    int u_fail = uvalid ? ctl.ufail[lane] : 0;
+    __syncwarp();         // every lane has its copy of the control block before any lane updates it below
+    // two dampings are equivalent when they give bitwise the same matrix J + shift(mu).  The entry
+    // with the smallest |J_kk| can only round to the same value if they differ by less than two of
+    // its ulps: cheap per-lane pre-test, the full comparison is rarely reached
+    auto maybe = [&](double ma, double mb) -> bool {
+        return ma == mb || !(fabs(ma - mb) > 4.5e-16 * (jdmin + fmax(ma, mb)));
+    };
+    auto equiv_full = [&](double ma, double mb) -> bool {
+        if (ma == mb) return true;
+        bool same = true;
+        for (int k = lane; k < s; k += 32) {
+            const double jd = jdv[k];
+            same = same && ((jd + shift_of(k, ma)) == (jd + shift_of(k, mb)));
+        }
+        return __all_sync(0xffffffffu, same);
+    };
+    auto look_real = [&](double mu, int, double, double& Q, int& id) -> bool {
+        const unsigned m = __ballot_sync(0xffffffffu, lane < nb0 && t_mu == mu);
+        id = -1;
+        if (m) id = __shfl_sync(0xffffffffu, t_slot, __ffs(m) - 1);
+        else {
+            const bool have_c = carry_row >= 0;
+            unsigned cm = __ballot_sync(0xffffffffu, (lane < nu0 || (lane == ID_CARRY && have_c)) && maybe(mu, u_mu));
+            while (cm && id < 0) {
+                const int u = __ffs(cm) - 1;
+                cm &= cm - 1;
+                if (equiv_full(mu, shfl(u_mu, u))) id = u;
+            }
+        }
+        if (id < 0) return false;
+        Q = shfl(u_Q, id);
+        ++ns; if (!__shfl_sync(0xffffffffu, u_fail, id)) ++nq;
+        return true;
+    };
+    const int done = lm_run(L, a.nu, a.max_mu, eps_nu, look_real) ? 1 : 0;
+    tick(PHT_REPLAY);
+    if (!done) {
+        // carry the live candidate of the old batch (its dv, y, chi2, S, damping and scratch row)
+        const int live = (L.phase == PH_WALK) ? L.dvnew : (L.phase == PH_PROBE ? L.dv : ID_NONE);
+        if (live >= 0 && live < MAXB) {
+            for (int i = lane; i < SP; i += 32) {
+                ctb[i] = tb[live * SP + i];
+                cy[i] = yb[live * SP + i];
+            }
+            const double lmu = shfl(u_mu, live), lQ = shfl(u_Q, live);
+            const int lfail = __shfl_sync(0xffffffffu, u_fail, live);
+            carry_row = ctl.urow[live];
+            if (lane == ID_CARRY) {
+                u_mu = lmu; u_Q = lQ; u_fail = lfail;
+                ctl.uQ[ID_CARRY] = lQ; ctl.uchi2[ID_CARRY] = ctl.uchi2[live]; ctl.uS[ID_CARRY] = ctl.uS[live];
+                ctl.ufail[ID_CARRY] = lfail; ctl.urow[ID_CARRY] = carry_row; ctl.umu[ID_CARRY] = lmu;
+            }
+            if (L.phase == PH_WALK) L.dvnew = ID_CARRY; else L.dv = ID_CARRY;
+        } else if (live == ID_NONE) {
+            carry_row = -1;
+            if (lane == 0) ctl.urow[ID_CARRY] = -1;
+        }
+        __syncwarp();
+        // plan: continue copies of the machine with pretended outcomes to list the next dampings.
+        // While the direction of this iteration's walk is not known yet (no probe outcome), BOTH
+        // branches are planned: the downward walk gets most of the budget (78 % of the iterations of
+        // the benchmark spectra walk down, 98 % of those that follow an upward one; tools/lm_trace.py),
+        // the upward walk the rest.  A pump (Q rises: mu *= nu until it does not) continues on the
+        // upward grid, so it is planned upward at full width.
+        int np = 0, npu = 0;
+        int budget = MAXB;
+        bool dir = true;
+        const bool undecided = (L.phase == PH_FIRST || L.phase == PH_PROBE);
+        if (undecided) { dir = false; budget = ctl.dir_up ? MAXB - 1 : MAXB - 2; }
+        else if (L.phase == PH_WALK) dir = (L.nuf == a.nu);
+        LM P = L;
+        const bool have_carry = carry_row >= 0;
+        const double cmu = shfl(u_mu, ID_CARRY), cQ = shfl(u_Q, ID_CARRY);
+        double p_mu = 0.0, pu_mu = 0.0, pu_q = 0.0;       // planned table entry / unique trial of this lane
+        int p_slot = 0;
+        auto find_or_add = [&](double mu, int kind, double Qref, double& Q, int& id) -> bool {
+            if (have_carry && maybe(mu, cmu) && equiv_full(mu, cmu)) { Q = cQ; id = ID_CARRY; return true; }
+            const unsigned m = __ballot_sync(0xffffffffu, lane < np && p_mu == mu);
+            if (m) {
+                const int u = __shfl_sync(0xffffffffu, p_slot, __ffs(m) - 1);
+                Q = shfl(pu_q, u); id = 100 + u;
+                return true;
+            }
+            unsigned cm = __ballot_sync(0xffffffffu, lane < npu && maybe(mu, pu_mu));
+            while (cm) {
+                const int u = __ffs(cm) - 1;
+                cm &= cm - 1;
+                if (equiv_full(mu, shfl(pu_mu, u))) {
+                    if (np < NTAB) { if (lane == np) { p_mu = mu; p_slot = u; } ++np; }
+                    Q = shfl(pu_q, u); id = 100 + u;
+                    return true;
+                }
+            }
+            if (npu >= budget || np == NTAB) return false;
+            double pv;
+            if (kind == 0) pv = isnan(Qref) ? 0.0 : Qref;                        // first trial / pump: "accepted"
+            else pv = Qref - (1.0 + fabs(Qref));                                  // walk: "still improving"
+            if (lane == np) { p_mu = mu; p_slot = npu; }
+            if (lane == npu) { pu_mu = mu; pu_q = pv; }
+            id = 100 + npu; Q = pv; ++np; ++npu;
+            return true;
+        };
+        auto look_plan = [&](double mu, int kind, double Qref, double& Q, int& id) -> bool {
+            if (!find_or_add(mu, kind, Qref, Q, id)) return false;
+            if (kind == 1) {
+                // the probe decides the direction: steer this run; a probe that IS the current candidate
+                // (bitwise the same shifted matrix) gives Q2 == Q1, i.e. "not lower"
+                if (id == P.dv) Q = Qref;
+                else Q = dir ? Qref - (1.0 + fabs(Qref)) : Qref + (1.0 + fabs(Qref));
+            }
+            return true;
+        };
+        // Fast paths for the three common situations: the dampings the machine would visit are written
+        // down directly, with the machine's own arithmetic (mu * nu, mu / (1/nu), mu * (1/nu), ...), instead
+        // of running it on pretended outcomes.  The plan is only a proposal -- the replay above decides
+        // everything on real values and re-plans when an entry is missing -- so a fast path can cost
+        // speculation efficiency but never change a result.
+        bool fast = false;
+        {
+            const double nu = a.nu, inu = 1.0 / a.nu;
+            auto add_unique = [&](double mu) {
+                if (lane == np) { p_mu = mu; p_slot = npu; }
+                if (lane == npu) { pu_mu = mu; pu_q = 0.0; }
+                ++np; ++npu;
+            };
+            if (L.phase == PH_PUMP && !have_carry && !maybe(L.mu * nu, L.mu)) {
+                double m = L.mu;                       // pump: mu *= nu until Q stops rising (:203-206)
+                for (int k = 0; k < MAXB; ++k) { m = m * nu; add_unique(m); }
+                fast = true;
+            } else if (L.phase == PH_WALK && have_carry && cmu == L.mu && !maybe(L.mu * L.nuf, L.mu)) {
+                double m = L.mu;                       // walk: mu *= nuf while Q improves (:226-233)
+                for (int k = 0; k < MAXB; ++k) { m = m * L.nuf; add_unique(m); }
+                fast = true;
+            } else if (L.phase == PH_FIRST && !have_carry && L.mu > 64.0 * eps_nu && L.mu < a.max_mu / 64.0 &&
+                       !maybe(L.mu * nu, L.mu)) {
+                const double m0 = L.mu, m1 = nu * m0;
+                add_unique(m0);                        // dv = solve(J + mu)            (:192)
+                add_unique(m1);                        // dv2 = solve(J + nu * mu)      (:209)
+                const int ndown = ctl.dir_up ? MAXB - 3 : MAXB - 4;
+                double m = m0 / inu;                   // probe lost: mu /= nuf, nuf = 1/nu   (:221-224)
+                for (int k = 0; k <= ndown; ++k) {
+                    m = m * inu;
+                    if (k == 0) {                      // first walk point = mu again, up to rounding
+                        if (m == m0) continue;
+                        if (equiv_full(m, m0)) { if (lane == np) { p_mu = m; p_slot = 0; } ++np; continue; }
+                    }
+                    if (npu < MAXB) add_unique(m);
+                }
+                m = m0 * nu;                           // probe won: mu *= nu, walk upward   (:214-218)
+                while (npu < MAXB) { m = m * nu; add_unique(m); }
+                fast = true;
+            }
+        }
+        if (!fast) {
+            lm_run(P, a.nu, a.max_mu, eps_nu, look_plan);
+            if (undecided && npu < MAXB) {         // the other branch with what is left of the batch
+                P = L;
+                dir = true;
+                budget = MAXB;
+                lm_run(P, a.nu, a.max_mu, eps_nu, look_plan);
+            }
+        }
+        if (lane < np) { ctl.bmu[lane] = p_mu; ctl.bslot[lane] = p_slot; }
+        if (lane < npu) {
+            ctl.umu[lane] = pu_mu;
+            ctl.urow[lane] = (carry_row >= 0 && lane >= carry_row) ? lane + 1 : lane;   // skip the carried row
+            ctl.ufail[lane] = 0;
+        }
+        if (lane == 0) { ctl.nb = np; ctl.nuniq = npu; ctl.ntrial += npu; ctl.nbatch += 1; }
+#ifdef MX_PLANPROF
+        // diagnostics: charge the planning time to slot 0 (fast paths) or 6 (generic planner); slot 4
+        // counts generic plans, slot 5 fast plans
+        if (timing && lane == 0) {
+            const long long t = clock64();
+            ctl.tph[fast ? 0 : 6] += t - ctl.t_last; ctl.t_last = t;
+            ctl.ntrial -= npu;                  // n_trial output = number of generic plans, by phase
+            ctl.ntrial += fast ? 0 : (L.phase == PH_FIRST ? 1 : L.phase == PH_PUMP ? 1000 : L.phase == PH_PROBE ? 1000000 : 100000000);
+        }
+#endif
+    }
+    if (lane == 0) { ctl.lm = L; ctl.ns = ns; ctl.nq = nq; ctl.conv = done; }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -429,6 +651,206 @@ __device__ __forceinline__ void lean_solve(const double* __restrict__ Lsm, const
         xr[jb] = quadreduce(fma(U[jb][0], z0, U[jb][1] * z1));
     }
     __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
+// Wide variants of the factorisation: the same left-looking blocked L D L^T, the same arithmetic per tile and per pivot as
+// lean_steps / lean_solve, but every tile of the factor lives in this warp's slice Lw of the global workspace (NTRI
+// tiles; a lane only ever reads back what it stored itself) and the block-column loops are run-time loops.  The
+// diagonal slot of block JB holds U = L_d^{-T}.  x replaces w = D^-1 L^-1 rhs in `zscr`.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 wtile(const double* Lw, int I, int J, int lane) {
+    return *reinterpret_cast<const double2*>(Lw + (size_t)tri(I, J) * 64 + 2 * lane);
+}
+template <int NT, bool FWD, class Load>
+__device__ __forceinline__ void wide_factor(Load& load, double* Lw, bool& ok, double& logdet, bool want_logdet, int r, int q,
+                                            int lane, const double* rhs, double* zscr, double* dinv) {
+    for (int JB = 0; JB < NT; ++JB) {
+        const int NC = NT - JB;
+        double C[NT][2];
+#pragma unroll
+        for (int i = 0; i < NT; ++i)
+            if (i < NC) { const double2 t = load(JB + i, JB); C[i][0] = t.x; C[i][1] = t.y; }
+        for (int K = 0; K < JB; ++K) {
+            const double2 y = wtile(Lw, JB, K, lane);
+            const double2 dk = *reinterpret_cast<const double2*>(dinv + 8 * K + 2 * q);
+            const double ys0 = y.x * dk.x, ys1 = y.y * dk.y;
+#pragma unroll
+            for (int i = 0; i < NT; ++i)
+                if (i < NC) {
+                    const double2 x = i == 0 ? y : wtile(Lw, JB + i, K, lane);
+                    mma_nt(C[i], -x.x, -x.y, ys0, ys1);
+                }
+        }
+        double E[2];
+        E[0] = (r == 2 * q) ? 1.0 : 0.0;
+        E[1] = (r == 2 * q + 1) ? 1.0 : 0.0;
+        double(&P0)[2] = C[0];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int jq = j >> 1, je = j & 1;
+            const double ajj = shfl(P0[je], 4 * j + jq);
+            const double lk0 = shfl(P0[je], 8 * q + jq);
+            const double lk1 = shfl(P0[je], 8 * q + 4 + jq);
+            const int src = (lane & ~3) | jq;
+            const double lp = shfl(P0[je], src);
+            const double le = shfl(E[je], src);
+            if (!(ajj > 0.0)) ok = false;
+            if (want_logdet) logdet += log(ajj);
+            const double inv = rcp_nr(ajj);
+            const double p0 = lp * lk0, p1 = lp * lk1, e0 = le * lk0, e1 = le * lk1;
+            if (2 * q > j) { P0[0] = fma(-p0, inv, P0[0]); E[0] = fma(-e0, inv, E[0]); }
+            if (2 * q + 1 > j) { P0[1] = fma(-p1, inv, P0[1]); E[1] = fma(-e1, inv, E[1]); }
+            if (lane == 0) dinv[8 * JB + j] = inv;
+        }
+        __syncwarp();
+        *reinterpret_cast<double2*>(Lw + (size_t)tri(JB, JB) * 64 + 2 * lane) = make_double2(E[0], E[1]);
+        if (NC > 1) {
+            const int s0 = 8 * q + (r >> 1), s1 = s0 + 4;
+            const double a0 = shfl(E[0], s0), b0 = shfl(E[1], s0);
+            const double a1 = shfl(E[0], s1), b1 = shfl(E[1], s1);
+            const double W0 = (r & 1) ? b0 : a0, W1 = (r & 1) ? b1 : a1;
+#pragma unroll
+            for (int i = 1; i < NT; ++i)
+                if (i < NC) {
+                    double c[2] = {0.0, 0.0};
+                    mma_nt(c, C[i][0], C[i][1], W0, W1);
+                    *reinterpret_cast<double2*>(Lw + (size_t)tri(JB + i, JB) * 64 + 2 * lane) = make_double2(c[0], c[1]);
+                }
+        }
+        if constexpr (FWD) {
+            double acc = 0.0;
+            for (int J = 0; J < JB; ++J) {
+                const double2 t = wtile(Lw, JB, J, lane);
+                const double2 wJ = *reinterpret_cast<const double2*>(zscr + 8 * J + 2 * q);
+                acc = fma(t.x, wJ.x, fma(t.y, wJ.y, acc));
+            }
+            double rr = rhs[8 * JB + r];
+            if (JB > 0) rr -= quadreduce(acc);
+            const double z0 = colreduce(E[0] * rr), z1 = colreduce(E[1] * rr);
+            const double2 dj = *reinterpret_cast<const double2*>(dinv + 8 * JB + 2 * q);
+            if (r == 0) *reinterpret_cast<double2*>(zscr + 8 * JB + 2 * q) = make_double2(z0 * dj.x, z1 * dj.y);
+            __syncwarp();
+        }
+    }
+}
+
+template <int NT>
+__device__ __forceinline__ void wide_solve(const double* Lw, const double* dinv, double* zscr, int r, int q, int lane) {
+    __syncwarp();
+    for (int jb = NT - 1; jb >= 0; --jb) {
+        double c0 = 0.0, c1 = 0.0;
+        for (int I = jb + 1; I < NT; ++I) {
+            const double2 t = wtile(Lw, I, jb, lane);
+            const double xI = zscr[8 * I + r];
+            c0 = fma(t.x, xI, c0);
+            c1 = fma(t.y, xI, c1);
+        }
+        const double2 w = *reinterpret_cast<const double2*>(zscr + 8 * jb + 2 * q);
+        double z0 = w.x, z1 = w.y;
+        if (jb < NT - 1) {
+            const double2 dj = *reinterpret_cast<const double2*>(dinv + 8 * jb + 2 * q);
+            z0 = fma(-dj.x, colreduce(c0), z0); z1 = fma(-dj.y, colreduce(c1), z1);
+        }
+        const double2 U = wtile(Lw, jb, jb, lane);
+        const double x = quadreduce(fma(U.x, z0, U.y * z1));
+        __syncwarp();                                      // every lane holds w_jb before x_jb takes its place
+        if (q == 0) zscr[8 * jb + r] = x;
+        __syncwarp();
+    }
+}
+
+// Wide H-pass: Z = V'^T diag(w) V' in blocks of 8 x 4 tiles per warp (accumulators in registers), every block a full
+// pass over V' in k order -- one warp per tile, hence one fixed summation order and no reduction between warps.
+template <int NT>
+__device__ __forceinline__ void hpass_wide(const double* __restrict__ Vt, const double* __restrict__ wrow, int n_kt, double* Zf,
+                                           int warp, int lane, int r, int q, int offY0, int offY1) {
+    constexpr int BI = 8, BJ = 4;
+    constexpr int NBI = (NT + BI - 1) / BI, NBJ = (NT + BJ - 1) / BJ;
+    int cnt = 0;
+    for (int bi = 0; bi < NBI; ++bi)
+        for (int bj = 0; bj < NBJ && BJ * bj <= BI * bi + BI - 1; ++bj, ++cnt) {
+            if (cnt % NWARP != warp) continue;
+            const int I0 = bi * BI, J0 = bj * BJ;
+            double z[BI][BJ][2];
+#pragma unroll
+            for (int i = 0; i < BI; ++i)
+#pragma unroll
+                for (int j = 0; j < BJ; ++j) { z[i][j][0] = 0.0; z[i][j][1] = 0.0; }
+            for (int kt = 0; kt < n_kt; ++kt) {
+                const double2 w = *reinterpret_cast<const double2*>(wrow + kt * 8 + 2 * q);
+                const double* tile = Vt + (size_t)kt * NT * 64;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int off = e ? offY1 : offY0;
+                    const double we = e ? w.y : w.x;
+                    double fi[BI], fj[BJ];
+#pragma unroll
+                    for (int i = 0; i < BI; ++i) fi[i] = (I0 + i < NT) ? we * tile[(I0 + i) * 64 + off] : 0.0;
+#pragma unroll
+                    for (int j = 0; j < BJ; ++j) fj[j] = (J0 + j < NT) ? tile[(J0 + j) * 64 + off] : 0.0;
+#pragma unroll
+                    for (int i = 0; i < BI; ++i)
+#pragma unroll
+                        for (int j = 0; j < BJ; ++j)
+                            if (J0 + j <= I0 + i && I0 + i < NT) dmma(z[i][j], fi[i], fj[j]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < BI; ++i)
+#pragma unroll
+                for (int j = 0; j < BJ; ++j) {
+                    const int I = I0 + i, J = J0 + j;
+                    if (J <= I && I < NT) {
+                        *reinterpret_cast<double2*>(Zf + (size_t)(I * NT + J) * 64 + 2 * lane) = make_double2(z[i][j][0], z[i][j][1]);
+                        if (I != J) {
+                            Zf[(size_t)(J * NT + I) * 64 + (2 * q) * 8 + r] = z[i][j][0];
+                            Zf[(size_t)(J * NT + I) * 64 + (2 * q + 1) * 8 + r] = z[i][j][1];
+                        }
+                    }
+                }
+        }
+    __syncthreads();
+}
+
+// The pointwise map of the cost pass for this lane's two omega rows: H = D e^x (plus-minus: D (e^x - e^-x)), w = dH/dx,
+// and the entropy terms added to sacc.
+template <bool pm>
+__device__ __forceinline__ void pointwise(double x0, double x1, double2 Dv, double (&Hv)[2], double (&Wv)[2], double& sacc) {
+    // the two (plus-minus: four) exponentials of this lane as independent straight-line chains; the rare
+    // huge arguments (overflowing pump trials) take the library path
+    double ex2[2], em2[2] = {0.0, 0.0};
+    if (__any_sync(0xffffffffu, mx::exp_is_special(x0) || mx::exp_is_special(x1))) {
+        ex2[0] = exp(x0); ex2[1] = exp(x1);
+        if (pm) { em2[0] = exp(-x0); em2[1] = exp(-x1); }
+    } else {
+        ex2[0] = mx::exp_main(x0); ex2[1] = mx::exp_main(x1);
+        if (pm) { em2[0] = mx::exp_main(-x0); em2[1] = mx::exp_main(-x1); }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double Dk = i ? Dv.y : Dv.x;
+        const double x = i ? x1 : x0;
+        const double ex = ex2[i];
+        double H, W, st_;
+        if (!pm) {
+            // H = D e^x ; S += H - D - H log(H/D), safelog clamp at 1e-100  (functions.py:53-56,508-510)
+            H = Dk * ex; W = H;
+            const double lg = (ex <= 1e-100) ? -230.25850929940458 : x;
+            st_ = H - Dk - H * lg;
+        } else {
+            // H = D (e^x - e^-x) ; w = D (e^x + e^-x) ; S = S_n(H+) + S_n(H-)   (functions.py:544-564,778-786)
+            const double em = em2[i];
+            const double Hp = Dk * ex, Hm = Dk * em;
+            H = Hp - Hm; W = Hp + Hm;
+            const double lp = (ex <= 1e-100) ? -230.25850929940458 : x;
+            const double lm = (em <= 1e-100) ? -230.25850929940458 : -x;
+            st_ = (Hp - Dk - Hp * lp) + (Hm - Dk - Hm * lm);
+        }
+        if (Dk == 0.0) { H = 0.0; W = 0.0; st_ = 0.0; }   // padded rows / missing tile
+        sacc += st_;
+        Hv[i] = H; Wv[i] = W;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -616,6 +1038,7 @@ __device__ __forceinline__ void hpass_body(const Pipe<NT>& pipe, const double* _
 // CTAs per SM the instantiation is compiled for: the target (MX_CTAS_PER_SM), or what its shared memory allows
 template <int NT>
 __host__ __device__ constexpr int ctas_per_sm() {
+    if (is_wide(NT)) return 1;                // the block accumulators of the wide H-pass need the full register file
     int n = (228 * 1024) / (Lay<NT>::total * (int)sizeof(double) + 1024);
     if (n > MX_CTAS_PER_SM) n = MX_CTAS_PER_SM;
     return n < 1 ? 1 : n;
@@ -645,6 +1068,14 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
     const size_t rowlen = (size_t)n_kt * 8;
     double* const wscr = a.scratch + (size_t)blockIdx.x * (pm ? 2 : 1) * NROWS * rowlen;   // [NROWS][rowlen] (+ H rows for plusminus)
     double* const hscr = wscr + (size_t)NROWS * rowlen;
+
+    constexpr bool WIDE = LY::WIDE;
+    // wide instantiations: Zfull, J and one factor per warp in this CTA's slice of the global workspace
+    double* const wZ = WIDE ? a.wide + (size_t)blockIdx.x * (size_t)a.wide_stride : nullptr;
+    double* const wJ = wZ + NT * NT * 64;
+    double* const wL = wJ + (size_t)(1 + warp) * NTRI * 64;
+    auto Zfull = [&]() -> double* { if constexpr (WIDE) return wZ; else return sm + LY::o_stage; };
+    auto Jtiles = [&]() -> double* { if constexpr (WIDE) return wJ; else return sm + LY::o_J; };
 
     const int offX = tile_off(r, 2 * q);
     const int offY0 = tile_off(2 * q + 0, r);
@@ -684,13 +1115,6 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
     auto tpass = [&]() {
         const unsigned g0 = ctl.gchunk;
         const int nuniq = ctl.nuniq;
-        pipe.begin(g0, Vsp);
-        double tA[NT][2];
-#pragma unroll
-        for (int jt = 0; jt < NT; ++jt) {
-            const double2 tv = *reinterpret_cast<const double2*>(sm + LY::o_tb + r * SP + 8 * jt + 2 * q);
-            tA[jt][0] = tv.x; tA[jt][1] = tv.y;
-        }
         double yacc[NT][2];
 #pragma unroll
         for (int jt = 0; jt < NT; ++jt) { yacc[jt][0] = 0.0; yacc[jt][1] = 0.0; }
@@ -708,6 +1132,41 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
             }
             return Dv;
         };
+        if constexpr (WIDE) {
+            __syncthreads();
+            for (int kt = warp; kt < n_kt; kt += NWARP) {          // V' straight from L2, the trial vectors from shared memory
+                const double* tile = Vsp + (size_t)kt * NT * 64;
+                const double2 Dv = loadD(kt);
+                double C0[2] = {0.0, 0.0}, C1[2] = {0.0, 0.0};
+#pragma unroll
+                for (int jt = 0; jt < NT; ++jt) {
+                    const double2 tv = *reinterpret_cast<const double2*>(sm + LY::o_tb + r * SP + 8 * jt + 2 * q);
+                    const double2 vv = *reinterpret_cast<const double2*>(tile + jt * 64 + offX);
+                    dmma(C0, tv.x, vv.x);
+                    dmma(C1, tv.y, vv.y);
+                }
+                double Hv[2], Wv[2];
+                const int k0 = kt * 8 + 2 * q;
+                pointwise<pm>(C0[0] + C1[0], C0[1] + C1[1], Dv, Hv, Wv, sacc);
+                if (live) {
+                    st_keep_v2(wrow + k0, Wv[0], Wv[1], keep_pol);
+                    if (pm) st_keep_v2(hrow + k0, Hv[0], Hv[1], keep_pol);
+                }
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int off = e ? offY1 : offY0;
+#pragma unroll
+                    for (int jt = 0; jt < NT; ++jt) dmma(yacc[jt], Hv[e], tile[jt * 64 + off]);
+                }
+            }
+        } else {
+        pipe.begin(g0, Vsp);
+        double tA[NT][2];
+#pragma unroll
+        for (int jt = 0; jt < NT; ++jt) {
+            const double2 tv = *reinterpret_cast<const double2*>(sm + LY::o_tb + r * SP + 8 * jt + 2 * q);
+            tA[jt][0] = tv.x; tA[jt][1] = tv.y;
+        }
         double2 Dv = loadD(warp);
         for (int c = 0; c < nch; ++c) {
 #ifdef MX_TPROF
@@ -727,41 +1186,7 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
             }
             double Hv[2], Wv[2];
             const int k0 = kt * 8 + 2 * q;
-            // the two (plus-minus: four) exponentials of this lane as independent straight-line chains; the rare
-            // huge arguments (overflowing pump trials) take the library path
-            const double x0 = C0[0] + C1[0], x1 = C0[1] + C1[1];
-            double ex2[2], em2[2] = {0.0, 0.0};
-            if (__any_sync(0xffffffffu, mx::exp_is_special(x0) || mx::exp_is_special(x1))) {
-                ex2[0] = exp(x0); ex2[1] = exp(x1);
-                if (pm) { em2[0] = exp(-x0); em2[1] = exp(-x1); }
-            } else {
-                ex2[0] = mx::exp_main(x0); ex2[1] = mx::exp_main(x1);
-                if (pm) { em2[0] = mx::exp_main(-x0); em2[1] = mx::exp_main(-x1); }
-            }
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const double Dk = i ? Dv.y : Dv.x;
-                const double x = i ? x1 : x0;
-                const double ex = ex2[i];
-                double H, W, st_;
-                if (!pm) {
-                    // H = D e^x ; S += H - D - H log(H/D), safelog clamp at 1e-100  (functions.py:53-56,508-510)
-                    H = Dk * ex; W = H;
-                    const double lg = (ex <= 1e-100) ? -230.25850929940458 : x;
-                    st_ = H - Dk - H * lg;
-                } else {
-                    // H = D (e^x - e^-x) ; w = D (e^x + e^-x) ; S = S_n(H+) + S_n(H-)   (functions.py:544-564,778-786)
-                    const double em = em2[i];
-                    const double Hp = Dk * ex, Hm = Dk * em;
-                    H = Hp - Hm; W = Hp + Hm;
-                    const double lp = (ex <= 1e-100) ? -230.25850929940458 : x;
-                    const double lm = (em <= 1e-100) ? -230.25850929940458 : -x;
-                    st_ = (Hp - Dk - Hp * lp) + (Hm - Dk - Hm * lm);
-                }
-                if (Dk == 0.0) { H = 0.0; W = 0.0; st_ = 0.0; }   // padded rows / missing tile
-                sacc += st_;
-                Hv[i] = H; Wv[i] = W;
-            }
+            pointwise<pm>(C0[0] + C1[0], C0[1] + C1[1], Dv, Hv, Wv, sacc);
             if (live && valid) {
                 st_keep_v2(wrow + k0, Wv[0], Wv[1], keep_pol);
                 if (pm) st_keep_v2(hrow + k0, Hv[0], Hv[1], keep_pol);
@@ -776,6 +1201,7 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
             }
             Dv = Dn;
             pipe.release(c, g0);
+        }
         }
         __syncthreads();                                   // staging area is free: reuse as yred[NWARP][8][SP]
         if (tid == 0) ctl.gchunk = g0 + nch;
@@ -816,15 +1242,20 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
 
     // ---- H-pass: Z = V'^T diag(w) V' with w from scratch row `row` -> Zfull (all NT x NT tiles, C layout) ----
     auto hpass = [&](int row) {
-        const unsigned g0 = ctl.gchunk;
-        pipe.begin(g0, Vsp);
-        const int kg = warp >> 1, th = warp & 1;
         const double* wrow = wscr + (size_t)row * rowlen;
-        double* Zf = sm + LY::o_stage;
-        if (th == 0) hpass_body<NT, 0>(pipe, Vsp, g0, wrow, kg, lane, r, q, offY0, offY1, Zf);
-        else hpass_body<NT, 1>(pipe, Vsp, g0, wrow, kg, lane, r, q, offY0, offY1, Zf);
-        if (tid == 0) ctl.gchunk = g0 + nch;
-        __syncthreads();
+        if constexpr (WIDE) {
+            __syncthreads();
+            hpass_wide<NT>(Vsp, wrow, n_kt, wZ, warp, lane, r, q, offY0, offY1);
+        } else {
+            const unsigned g0 = ctl.gchunk;
+            pipe.begin(g0, Vsp);
+            const int kg = warp >> 1, th = warp & 1;
+            double* Zf = sm + LY::o_stage;
+            if (th == 0) hpass_body<NT, 0>(pipe, Vsp, g0, wrow, kg, lane, r, q, offY0, offY1, Zf);
+            else hpass_body<NT, 1>(pipe, Vsp, g0, wrow, kg, lane, r, q, offY0, offY1, Zf);
+            if (tid == 0) ctl.gchunk = g0 + nch;
+            __syncthreads();
+        }
     };
 
     // ---- gradient: u = eta Xi (Xi y - g~) + alpha v ; f = Z u (or u for Bryan) ; maxf -------------------
@@ -845,7 +1276,7 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
         }
         __syncthreads();
         if (!bryan) {
-            const double* Zf = sm + LY::o_stage;
+            const double* Zf = Zfull();
             for (int I = warp; I < NT; I += NWARP) {
                 double cf[2] = {0.0, 0.0};
 #pragma unroll
@@ -869,7 +1300,7 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
 
     // ---- J = eta Z Lambda Z + alpha Z (lower tiles, C layout) and its diagonal ---------------------------
     auto form_J = [&]() {
-        const double* Zf = sm + LY::o_stage;
+        const double* Zf = Zfull();
         const double alpha = ctl.alpha;
         for (int t = warp; t < NTRI; t += NWARP) {
             int I = 0;
@@ -902,7 +1333,7 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
                 if (8 * I + r >= s || 8 * J + 2 * q >= s) c[0] = 0.0;
                 if (8 * I + r >= s || 8 * J + 2 * q + 1 >= s) c[1] = 0.0;
             }
-            *reinterpret_cast<double2*>(sm + LY::o_J + t * 64 + 2 * lane) = make_double2(c[0], c[1]);
+            *reinterpret_cast<double2*>(Jtiles() + (size_t)t * 64 + 2 * lane) = make_double2(c[0], c[1]);
         }
         __syncthreads();
         if (warp == 0) {
@@ -932,12 +1363,12 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
         const int nuniq = ctl.nuniq;
         // every solver warp factorises one shifted Hessian at a time; the strictly-lower tiles of the leading block
         // columns are parked in this warp's slice of the idle staging ring
-        constexpr int NSOLVE = solver_warps(NT);
+        constexpr int NSOLVE = WIDE ? NWARP : solver_warps(NT);
         double* const Lsm = sm + LY::o_stage + LY::NST * LY::STAGE_D - (warp + 1) * LN::NSMT * 64;
         for (int u = warp; u < nuniq && warp < NSOLVE; u += NSOLVE) {
             const double mu = ctl.umu[u];
             auto load = [&](int I, int J) -> double2 {
-                double2 v = *reinterpret_cast<const double2*>(sm + LY::o_J + tri(I, J) * 64 + 2 * lane);
+                double2 v = *reinterpret_cast<const double2*>(Jtiles() + (size_t)tri(I, J) * 64 + 2 * lane);
                 if (I == J) {
                     const int i0 = 8 * I + r;
                     if (i0 < s) {
@@ -948,16 +1379,25 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
                 }
                 return v;
             };
-            double R[LN::RDIM][2];
-            double U[NT][2];
             bool ok = true;
             double ld = 0.0;
             double* const trow = sm + LY::o_tb + u * SP;          // scratch for the forward substitution, then t = v - dv
             double* const dinv = sm + LY::o_yb + u * SP;          // 1 / d of the L D L^T factorisation (yb is dead here)
-            lean_steps<NT, 0, true>(load, Lsm, R, U, ok, ld, false, r, q, lane, sm + LY::o_rhs, trow, dinv);
-            ok = __all_sync(0xffffffffu, ok);
             double xr[NT];
-            lean_solve<NT>(Lsm, R, U, dinv, xr, r, q, lane, trow);
+            if constexpr (WIDE) {
+                wide_factor<NT, true>(load, wL, ok, ld, false, r, q, lane, sm + LY::o_rhs, trow, dinv);
+                ok = __all_sync(0xffffffffu, ok);
+                wide_solve<NT>(wL, dinv, trow, r, q, lane);
+#pragma unroll
+                for (int I = 0; I < NT; ++I) xr[I] = trow[8 * I + r];
+                __syncwarp();
+            } else {
+                double R[LN::RDIM][2];
+                double U[NT][2];
+                lean_steps<NT, 0, true>(load, Lsm, R, U, ok, ld, false, r, q, lane, sm + LY::o_rhs, trow, dinv);
+                ok = __all_sync(0xffffffffu, ok);
+                lean_solve<NT>(Lsm, R, U, dinv, xr, r, q, lane, trow);
+            }
             if (q == 0) {
 #pragma unroll
                 for (int I = 0; I < NT; ++I) {
@@ -973,7 +1413,7 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
 
     // ---- log det(I + eta Xi Z Xi / alpha) by warp 0 (probabilities.py:76-85 via Sylvester) -----------------
     auto logdet_prob = [&]() -> double {       // warp 0 only; returns NaN on a failed factorisation
-        const double* Zf = sm + LY::o_stage;
+        const double* Zf = Zfull();
         auto entry = [&](int I, int J) -> double2 {
             const double2 z = *reinterpret_cast<const double2*>(Zf + (I * NT + J) * 64 + 2 * lane);
             const int i0 = 8 * I + r, j0 = 8 * J + 2 * q;
@@ -986,12 +1426,16 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
             if (i0 == j0 + 1) m1 += 1.0;
             return make_double2(m0, m1);
         };
-        double U[NT][2];
         bool ok = true;
         double ld = 0.0;
-        double* const Lsm = sm + LY::o_J;                  // J of the finished iteration is dead: park the tiles there
-        double R[LN::RDIM][2];
-        lean_steps<NT, 0, false>(entry, Lsm, R, U, ok, ld, true, r, q, lane, nullptr, nullptr, sm + LY::o_yb);
+        if constexpr (WIDE) {                              // J of the finished iteration is dead: park the tiles there
+            wide_factor<NT, false>(entry, wJ, ok, ld, true, r, q, lane, nullptr, nullptr, sm + LY::o_yb);
+        } else {
+            double U[NT][2];
+            double* const Lsm = sm + LY::o_J;
+            double R[LN::RDIM][2];
+            lean_steps<NT, 0, false>(entry, Lsm, R, U, ok, ld, true, r, q, lane, nullptr, nullptr, sm + LY::o_yb);
+        }
         ok = __all_sync(0xffffffffu, ok);
         return ok ? ld : nan("");
     };
@@ -1120,204 +1564,9 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
             if (tid == 0) { ctl.lm.Q0 = ctl.lm.Q1; ctl.lm.phase = PH_FIRST; ctl.nb = 0; ctl.nuniq = 0; ctl.urow[ID_CARRY] = -1; ctl.ns_it0 = ctl.ns; }
             __syncthreads();
             for (;;) {
-                if (warp == 0) {
-                    // The whole warp runs the (scalar, warp-uniform) state machine.  The tables live in registers:
-                    // lane i holds table entry i (damping, unique trial) and unique trial i (damping, Q, failed);
-                    // searches are ballots, reads are shuffles.
-                    LM L = ctl.lm;
-                    int ns = ctl.ns, nq = ctl.nq;
-                    const double* jdv = sm + LY::o_jd;
-                    const double jdmin = ctl.jdmin;
-                    const int nb0 = ctl.nb, nu0 = ctl.nuniq;
-                    int carry_row = ctl.urow[ID_CARRY];
-                    double t_mu = lane < nb0 ? ctl.bmu[lane] : 0.0;
-                    int t_slot = lane < nb0 ? ctl.bslot[lane] : 0;
-                    const bool uvalid = lane < nu0 || (lane == ID_CARRY && carry_row >= 0);
-                    double u_mu = uvalid ? ctl.umu[lane] : 0.0;
-                    double u_Q = uvalid ? ctl.uQ[lane] : 0.0;
-                    int u_fail = uvalid ? ctl.ufail[lane] : 0;
-                    __syncwarp();         // every lane has its copy of the control block before any lane updates it below
-                    // two dampings are equivalent when they give bitwise the same matrix J + shift(mu).  The entry
-                    // with the smallest |J_kk| can only round to the same value if they differ by less than two of
-                    // its ulps: cheap per-lane pre-test, the full comparison is rarely reached
-                    auto maybe = [&](double ma, double mb) -> bool {
-                        return ma == mb || !(fabs(ma - mb) > 4.5e-16 * (jdmin + fmax(ma, mb)));
-                    };
-                    auto equiv_full = [&](double ma, double mb) -> bool {
-                        if (ma == mb) return true;
-                        bool same = true;
-                        for (int k = lane; k < s; k += 32) {
-                            const double jd = jdv[k];
-                            same = same && ((jd + shift_of(k, ma)) == (jd + shift_of(k, mb)));
-                        }
-                        return __all_sync(0xffffffffu, same);
-                    };
-                    auto look_real = [&](double mu, int, double, double& Q, int& id) -> bool {
-                        const unsigned m = __ballot_sync(0xffffffffu, lane < nb0 && t_mu == mu);
-                        id = -1;
-                        if (m) id = __shfl_sync(0xffffffffu, t_slot, __ffs(m) - 1);
-                        else {
-                            const bool have_c = carry_row >= 0;
-                            unsigned cm = __ballot_sync(0xffffffffu, (lane < nu0 || (lane == ID_CARRY && have_c)) && maybe(mu, u_mu));
-                            while (cm && id < 0) {
-                                const int u = __ffs(cm) - 1;
-                                cm &= cm - 1;
-                                if (equiv_full(mu, shfl(u_mu, u))) id = u;
-                            }
-                        }
-                        if (id < 0) return false;
-                        Q = shfl(u_Q, id);
-                        ++ns; if (!__shfl_sync(0xffffffffu, u_fail, id)) ++nq;
-                        return true;
-                    };
-                    const int done = lm_run(L, a.nu, a.max_mu, eps_nu, look_real) ? 1 : 0;
-                    tick(PHT_REPLAY);
-                    if (!done) {
-                        // carry the live candidate of the old batch (its dv, y, chi2, S, damping and scratch row)
-                        const int live = (L.phase == PH_WALK) ? L.dvnew : (L.phase == PH_PROBE ? L.dv : ID_NONE);
-                        if (live >= 0 && live < MAXB) {
-                            for (int i = lane; i < SP; i += 32) {
-                                sm[LY::o_ctb + i] = sm[LY::o_tb + live * SP + i];
-                                sm[LY::o_cy + i] = sm[LY::o_yb + live * SP + i];
-                            }
-                            const double lmu = shfl(u_mu, live), lQ = shfl(u_Q, live);
-                            const int lfail = __shfl_sync(0xffffffffu, u_fail, live);
-                            carry_row = ctl.urow[live];
-                            if (lane == ID_CARRY) {
-                                u_mu = lmu; u_Q = lQ; u_fail = lfail;
-                                ctl.uQ[ID_CARRY] = lQ; ctl.uchi2[ID_CARRY] = ctl.uchi2[live]; ctl.uS[ID_CARRY] = ctl.uS[live];
-                                ctl.ufail[ID_CARRY] = lfail; ctl.urow[ID_CARRY] = carry_row; ctl.umu[ID_CARRY] = lmu;
-                            }
-                            if (L.phase == PH_WALK) L.dvnew = ID_CARRY; else L.dv = ID_CARRY;
-                        } else if (live == ID_NONE) {
-                            carry_row = -1;
-                            if (lane == 0) ctl.urow[ID_CARRY] = -1;
-                        }
-                        __syncwarp();
-                        // plan: continue copies of the machine with pretended outcomes to list the next dampings.
-                        // While the direction of this iteration's walk is not known yet (no probe outcome), BOTH
-                        // branches are planned: the downward walk gets most of the budget (78 % of the iterations of
-                        // the benchmark spectra walk down, 98 % of those that follow an upward one; tools/lm_trace.py),
-                        // the upward walk the rest.  A pump (Q rises: mu *= nu until it does not) continues on the
-                        // upward grid, so it is planned upward at full width.
-                        int np = 0, npu = 0;
-                        int budget = MAXB;
-                        bool dir = true;
-                        const bool undecided = (L.phase == PH_FIRST || L.phase == PH_PROBE);
-                        if (undecided) { dir = false; budget = ctl.dir_up ? MAXB - 1 : MAXB - 2; }
-                        else if (L.phase == PH_WALK) dir = (L.nuf == a.nu);
-                        LM P = L;
-                        const bool have_carry = carry_row >= 0;
-                        const double cmu = shfl(u_mu, ID_CARRY), cQ = shfl(u_Q, ID_CARRY);
-                        double p_mu = 0.0, pu_mu = 0.0, pu_q = 0.0;       // planned table entry / unique trial of this lane
-                        int p_slot = 0;
-                        auto find_or_add = [&](double mu, int kind, double Qref, double& Q, int& id) -> bool {
-                            if (have_carry && maybe(mu, cmu) && equiv_full(mu, cmu)) { Q = cQ; id = ID_CARRY; return true; }
-                            const unsigned m = __ballot_sync(0xffffffffu, lane < np && p_mu == mu);
-                            if (m) {
-                                const int u = __shfl_sync(0xffffffffu, p_slot, __ffs(m) - 1);
-                                Q = shfl(pu_q, u); id = 100 + u;
-                                return true;
-                            }
-                            unsigned cm = __ballot_sync(0xffffffffu, lane < npu && maybe(mu, pu_mu));
-                            while (cm) {
-                                const int u = __ffs(cm) - 1;
-                                cm &= cm - 1;
-                                if (equiv_full(mu, shfl(pu_mu, u))) {
-                                    if (np < NTAB) { if (lane == np) { p_mu = mu; p_slot = u; } ++np; }
-                                    Q = shfl(pu_q, u); id = 100 + u;
-                                    return true;
-                                }
-                            }
-                            if (npu >= budget || np == NTAB) return false;
-                            double pv;
-                            if (kind == 0) pv = isnan(Qref) ? 0.0 : Qref;                        // first trial / pump: "accepted"
-                            else pv = Qref - (1.0 + fabs(Qref));                                  // walk: "still improving"
-                            if (lane == np) { p_mu = mu; p_slot = npu; }
-                            if (lane == npu) { pu_mu = mu; pu_q = pv; }
-                            id = 100 + npu; Q = pv; ++np; ++npu;
-                            return true;
-                        };
-                        auto look_plan = [&](double mu, int kind, double Qref, double& Q, int& id) -> bool {
-                            if (!find_or_add(mu, kind, Qref, Q, id)) return false;
-                            if (kind == 1) {
-                                // the probe decides the direction: steer this run; a probe that IS the current candidate
-                                // (bitwise the same shifted matrix) gives Q2 == Q1, i.e. "not lower"
-                                if (id == P.dv) Q = Qref;
-                                else Q = dir ? Qref - (1.0 + fabs(Qref)) : Qref + (1.0 + fabs(Qref));
-                            }
-                            return true;
-                        };
-                        // Fast paths for the three common situations: the dampings the machine would visit are written
-                        // down directly, with the machine's own arithmetic (mu * nu, mu / (1/nu), mu * (1/nu), ...), instead
-                        // of running it on pretended outcomes.  The plan is only a proposal -- the replay above decides
-                        // everything on real values and re-plans when an entry is missing -- so a fast path can cost
-                        // speculation efficiency but never change a result.
-                        bool fast = false;
-                        {
-                            const double nu = a.nu, inu = 1.0 / a.nu;
-                            auto add_unique = [&](double mu) {
-                                if (lane == np) { p_mu = mu; p_slot = npu; }
-                                if (lane == npu) { pu_mu = mu; pu_q = 0.0; }
-                                ++np; ++npu;
-                            };
-                            if (L.phase == PH_PUMP && !have_carry && !maybe(L.mu * nu, L.mu)) {
-                                double m = L.mu;                       // pump: mu *= nu until Q stops rising (:203-206)
-                                for (int k = 0; k < MAXB; ++k) { m = m * nu; add_unique(m); }
-                                fast = true;
-                            } else if (L.phase == PH_WALK && have_carry && cmu == L.mu && !maybe(L.mu * L.nuf, L.mu)) {
-                                double m = L.mu;                       // walk: mu *= nuf while Q improves (:226-233)
-                                for (int k = 0; k < MAXB; ++k) { m = m * L.nuf; add_unique(m); }
-                                fast = true;
-                            } else if (L.phase == PH_FIRST && !have_carry && L.mu > 64.0 * eps_nu && L.mu < a.max_mu / 64.0 &&
-                                       !maybe(L.mu * nu, L.mu)) {
-                                const double m0 = L.mu, m1 = nu * m0;
-                                add_unique(m0);                        // dv = solve(J + mu)            (:192)
-                                add_unique(m1);                        // dv2 = solve(J + nu * mu)      (:209)
-                                const int ndown = ctl.dir_up ? MAXB - 3 : MAXB - 4;
-                                double m = m0 / inu;                   // probe lost: mu /= nuf, nuf = 1/nu   (:221-224)
-                                for (int k = 0; k <= ndown; ++k) {
-                                    m = m * inu;
-                                    if (k == 0) {                      // first walk point = mu again, up to rounding
-                                        if (m == m0) continue;
-                                        if (equiv_full(m, m0)) { if (lane == np) { p_mu = m; p_slot = 0; } ++np; continue; }
-                                    }
-                                    if (npu < MAXB) add_unique(m);
-                                }
-                                m = m0 * nu;                           // probe won: mu *= nu, walk upward   (:214-218)
-                                while (npu < MAXB) { m = m * nu; add_unique(m); }
-                                fast = true;
-                            }
-                        }
-                        if (!fast) {
-                            lm_run(P, a.nu, a.max_mu, eps_nu, look_plan);
-                            if (undecided && npu < MAXB) {         // the other branch with what is left of the batch
-                                P = L;
-                                dir = true;
-                                budget = MAXB;
-                                lm_run(P, a.nu, a.max_mu, eps_nu, look_plan);
-                            }
-                        }
-                        if (lane < np) { ctl.bmu[lane] = p_mu; ctl.bslot[lane] = p_slot; }
-                        if (lane < npu) {
-                            ctl.umu[lane] = pu_mu;
-                            ctl.urow[lane] = (carry_row >= 0 && lane >= carry_row) ? lane + 1 : lane;   // skip the carried row
-                            ctl.ufail[lane] = 0;
-                        }
-                        if (lane == 0) { ctl.nb = np; ctl.nuniq = npu; ctl.ntrial += npu; ctl.nbatch += 1; }
-#ifdef MX_PLANPROF
-                        // diagnostics: charge the planning time to slot 0 (fast paths) or 6 (generic planner); slot 4
-                        // counts generic plans, slot 5 fast plans
-                        if (timing && lane == 0) {
-                            const long long t = clock64();
-                            ctl.tph[fast ? 0 : 6] += t - ctl.t_last; ctl.t_last = t;
-                            ctl.ntrial -= npu;                  // n_trial output = number of generic plans, by phase
-                            ctl.ntrial += fast ? 0 : (L.phase == PH_FIRST ? 1 : L.phase == PH_PUMP ? 1000 : L.phase == PH_PROBE ? 1000000 : 100000000);
-                        }
-#endif
-                    }
-                    if (lane == 0) { ctl.lm = L; ctl.ns = ns; ctl.nq = nq; ctl.conv = done; }
-                }
+                if (warp == 0)
+                    replay_and_plan<MARQ>(ctl, a, eps_nu, s, SP, lane, sm + LY::o_jd, sm + LY::o_tb, sm + LY::o_yb, sm + LY::o_ctb,
+                                          sm + LY::o_cy, timing, tick);
                 __syncthreads();
                 tick(PHT_PLAN);
                 if (ctl.conv) break;

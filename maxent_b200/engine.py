@@ -127,7 +127,7 @@ class SharedProblem(object):
                     Xi = torch.cat([Xi, torch.zeros(s - k, dtype=f64, device=dev)])
             # The left vectors of singular values near the rounding floor come out of a one-sided Jacobi (or any
             # SVD) with an orthogonality error ~ eps * S[0] / S[i]; chi2 = |Xi y - Q^T g|^2 + |(1 - Q Q^T) g|^2
-            # needs Q^T Q = 1.  Two Gram-Schmidt passes in order of decreasing singular value leave the
+            # needs Q^T Q = 1.  Re-orthogonalised Gram-Schmidt in order of decreasing singular value leave the
             # well-determined columns untouched (to rounding) and move the others by an amount whose effect on
             # K H is ~ 1e-2 * S[i] -- far below the data error.
             Q = self._reorthonormalize(Q)
@@ -160,16 +160,15 @@ class SharedProblem(object):
             self.engine = int(engine)
             self.config = _lib.sweep_config(s, self.engine)
 
-    @staticmethod
-    def _reorthonormalize(Q):
-        Q = Q.clone()
-        for j in range(Q.shape[1]):
-            q = Q[:, j]
-            if j:
-                for _ in range(2):
-                    q = q - Q[:, :j] @ (Q[:, :j].transpose(0, 1) @ q)
-            Q[:, j] = q / q.norm()
-        return Q
+    def _reorthonormalize(self, Q):
+        """Columns of Q made orthonormal in order, on the device in one launch (mx_gram_schmidt_rows)."""
+        torch = _torch()
+        Qt = Q.transpose(0, 1).contiguous()
+        stream = ctypes.c_void_p(torch.cuda.current_stream(Q.device).cuda_stream)
+        with torch.cuda.device(Q.device):
+            _lib.check(self.lib.mx_gram_schmidt_rows(_ptr(Qt), int(Qt.shape[1]), int(Qt.shape[0]), 0.0, stream),
+                       "mx_gram_schmidt_rows")
+        return Qt.transpose(0, 1).contiguous()
 
     def _svd(self, K, method):
         torch = _torch()
@@ -223,6 +222,7 @@ def matmul_host(A, B, device=None):
 
 SVD_DIRECT_MAX = 160      # matrices with min(m, n) up to this get the full one-sided Jacobi (mx_svd_jacobi)
 SVD_FIRST_RANK = 128      # first guess of the number of leading triplets of a larger matrix (mx_svd_truncated)
+SVD_RANGE_MAX = 512       # columns the range finder of mx_svd_truncated handles (one-CTA Gram-Schmidt)
 SVD_FLOOR = 1.e-15        # a returned singular value below SVD_FLOOR * S[0] is at the rounding floor of the matrix
 SVD_SEED = 0x6d6178656e74  # the random range finder is reproducible
 
@@ -233,7 +233,8 @@ def device_svd(K):
     Small matrices (min(m, n) <= SVD_DIRECT_MAX): full one-sided Jacobi, k = min(m, n).  Larger ones: the leading
     triplets only (mx_svd_truncated), with k doubled until at least eight of the returned singular values sit at the
     rounding floor -- then K = U S V^T holds to eps * S[0] and nothing above the floor is missing; a matrix that is
-    not numerically rank deficient ends at k = min(m, n), i.e. with the full SVD.  ``info`` says which route ran."""
+    not numerically rank deficient ends at k = min(m, n), i.e. with the full SVD (through the same range finder up to
+    SVD_RANGE_MAX columns, plain Jacobi on K above).  ``info`` says which route ran."""
     torch = _torch()
     lib = _lib.load()
     dev = K.device
@@ -258,7 +259,8 @@ def device_svd(K):
         return full()
     Kc = K.contiguous()
     p = SVD_FIRST_RANK
-    while p < kmin:
+    while min(p, kmin) <= SVD_RANGE_MAX:
+        p = min(p, kmin)
         U = torch.empty((m, p), dtype=f64, device=dev)
         S = torch.empty((p,), dtype=f64, device=dev)
         V = torch.empty((n, p), dtype=f64, device=dev)
@@ -266,6 +268,11 @@ def device_svd(K):
         work = torch.empty((nwork,), dtype=f64, device=dev)
         _lib.check(lib.mx_svd_truncated(_ptr(Kc), m, n, p, _ptr(U), _ptr(S), _ptr(V), _ptr(work), SVD_SEED, stream),
                    "mx_svd_truncated")
+        if p == kmin:
+            # not rank deficient: the range finder spans everything, K Q has graded columns -- the form in which a
+            # one-sided Jacobi converges in a few sweeps (on K itself, columns of equal norm and a condition number of
+            # 1e12, sixty sweeps are not enough beyond ~200 columns)
+            return U, S, V, "range finder + jacobi, all %d columns" % p
         Sh = S.cpu()
         if int((Sh > SVD_FLOOR * float(Sh[0])).sum()) <= p - 8:
             return U, S, V, "truncated, %d leading triplets" % p

@@ -26,6 +26,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import maxent_oracle as mo  # noqa: E402
 
 _P = {}
+PERTURBATIONS = (1, 2, 3, 4, 5)      # see _perturbed
 
 
 def kresolved_inputs(n_tau, n_omega, kpoints, rows, seed=3):
@@ -56,21 +57,27 @@ def _init(n_tau, n_omega, n_alpha, n_spectra, thr, seed):
 def _perturbed(task):
     """One rounding-level perturbation of the oracle run of spectrum b (SURVEY.md 8(c) tier T4: the oracle's own
     reproducibility): v = 1, 2: G * (1 +- 1e-15); v = 3: the other LAPACK SVD driver (gesvd instead of numpy's gesdd --
-    the singular vectors next to the cut are only determined to ~eps * S[0] / S[k])."""
+    the singular vectors next to the cut are only determined to ~eps * S[0] / S[k]); v = 4: every entry of
+    the kernel matrix moved by +-1e-15 relative (the rounding of the kernel itself); v = 5: G * (1 + 2e-15)."""
     b, v = task
     pr = _P["pr"]
     G = pr["G"][b]
+    K = pr["K"]
     svd = None
     if v == 1:
         G = G * (1.0 + 1.e-15)
     elif v == 2:
         G = G * (1.0 - 1.e-15)
+    elif v == 4:
+        K = K * (1.0 + 1.e-15 * np.random.default_rng(1000 + b).choice([-1.0, 1.0], size=K.shape))
+    elif v == 5:
+        G = G * (1.0 + 2.e-15)
     else:
         import scipy.linalg
         U, S, Vh = scipy.linalg.svd(pr["K"], full_matrices=False, lapack_driver="gesvd")
         keep = S >= _P["thr"]
         svd = (U[:, keep], S[keep], Vh.T[:, keep])
-    o2 = mo.maxent_loop(pr["K"], G, pr["err"], pr["omega"], _P["mesh"], reduce_singular_space=_P["thr"], fast_d2=True,
+    o2 = mo.maxent_loop(K, G, pr["err"], pr["omega"], _P["mesh"], reduce_singular_space=_P["thr"], fast_d2=True,
                         analyzers=False, svd=svd)
     return dict(b=b, v=v, A=o2["A"], chi2=o2["chi2"])
 
@@ -104,10 +111,10 @@ def run(n_tau, n_omega, n_alpha, spectra, procs, thr=1e-11, seed=5, dump=None, k
         rows = [_one(b) for b in range(spectra)]
     else:
         with ctx.Pool(procs, initializer=_init, initargs=(n_tau, n_omega, n_alpha, spectra, thr, seed)) as pool:
-            pert = pool.map_async(_perturbed, [(b, v) for v in (1, 2, 3) for b in range(spectra)], chunksize=1) if noise else None
+            pert = pool.map_async(_perturbed, [(b, v) for v in PERTURBATIONS for b in range(spectra)], chunksize=1) if noise else None
             rows = pool.map(_one, range(spectra), chunksize=1)
             pert = pert.get() if pert is not None else []
-        for r in pert:                       # noise floor = largest movement over the three perturbations
+        for r in pert:                       # noise floor = largest movement over the perturbations
             a = rows[r["b"]]["arrays"]
             nA = np.max(np.abs(r["A"] - a["A"]), axis=1) / np.max(np.abs(a["A"]), axis=1)
             nc = np.abs(r["chi2"] / a["chi2"] - 1.0)
@@ -145,7 +152,7 @@ def main():
     ap.add_argument("--krows", default="", help="comma-separated k values to run (with --kpoints)")
     ap.add_argument("--first", type=int, default=0, help="first row of the benchmark batch to run (rows of another rank's shard)")
     ap.add_argument("--noise-floor", action="store_true",
-                    help="with --dump and --procs > 1: also run three rounding-level perturbations of every spectrum")
+                    help="with --dump and --procs > 1: also run the rounding-level perturbations of every spectrum")
     a = ap.parse_args()
     procs = a.procs or (os.cpu_count() or 1)
     spectra = a.spectra or procs

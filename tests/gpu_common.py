@@ -26,6 +26,24 @@ def running_max(x, half=2):
     return np.array([np.max(x[max(0, i - half):i + half + 1]) for i in range(len(x))])
 
 
+# rounding-level perturbations of the data used to measure the oracle's own noise floor where it is run live
+EPS = (1e-15, -1e-15, 2e-15, -2e-15)
+
+
+def oracle_floor(base, run):
+    """Noise floor of a live oracle result `base`: the largest movement of A and chi2, per alpha, over the runs
+    run(1 + eps) for the rounding-level perturbations EPS (one sample is a noisy estimate of the floor, and the small-alpha
+    tail amplifies rounding differences by many orders of magnitude).  Returns (noise_A, noise_chi2), running maxima
+    over +-2 alphas."""
+    nA = np.zeros(len(base["chi2"]))
+    nc = np.zeros(len(base["chi2"]))
+    for e in EPS:
+        o2 = run(1.0 + e)
+        nA = np.maximum(nA, rel_A(o2["A"], base["A"]))
+        nc = np.maximum(nc, np.abs(o2["chi2"] / base["chi2"] - 1))
+    return running_max(nA), running_max(nc)
+
+
 def tolerances(g, field):
     """Per-alpha tolerance: 1e-8 where the reference is reproducible to better than that, else
     10x its own measured noise floor (running max over +-2 alphas: one sample is a noisy estimate)."""

@@ -340,17 +340,17 @@ def test_rank_deficient_covariance():
 
 
 def test_rank_above_the_fused_limit_raises():
-    """A kernel whose numerical rank exceeds MX_MAX_NSV is an error (the reference keeps every S >= threshold,
+    """A kernel whose numerical rank exceeds MX_MAX_NSV (256) is an error (the reference keeps every S >= threshold,
     python/kernels.py:101-122; a silent truncation would change A), unless the caller asks for the truncation."""
     from maxent_b200 import engine, _lib
     rng = np.random.RandomState(2)
-    K = rng.randn(200, 100)
-    om = np.linspace(-5, 5, 100)
+    K = rng.randn(400, 300)
+    om = np.linspace(-5, 5, 300)
     with pytest.raises(_lib.MaxEntLibraryError):
         engine.SharedProblem(K, 1e-2, mo.flat_default_model(om), mo.omega_delta(om), reduce_singular_space=1e-14)
     prob = engine.SharedProblem(K, 1e-2, mo.flat_default_model(om), mo.omega_delta(om), reduce_singular_space=1e-14,
                                 max_nsv=64)
-    assert prob.n_sv == 64 and prob.n_sv_uncapped == 100
+    assert prob.n_sv == 64 and prob.n_sv_uncapped == 300
 
 
 def test_per_spectrum_error_models_in_one_launch():
@@ -371,8 +371,7 @@ def test_per_spectrum_error_models_in_one_launch():
         return j
 
     def check(out, b, o, what):
-        o2 = o["rerun"]
-        tol = np.maximum(1e-8, 10 * gc.running_max(gc.rel_A(o2["A"], o["A"])))
+        tol = np.maximum(1e-8, 10 * o["noise_A"])
         dA = gc.rel_A(out.A(b), o["A"])
         assert np.all(dA <= tol), (what, b, dA / tol)
         np.testing.assert_allclose(out.chi2[b], o["chi2"], rtol=1e-7, err_msg="%s %d" % (what, b))
@@ -381,7 +380,8 @@ def test_per_spectrum_error_models_in_one_launch():
 
     def oracle(K, G, err, svd=None):
         o = mo.maxent_loop(K, G, err, pr["omega"], mesh, reduce_singular_space=1e-10, svd=svd)
-        o["rerun"] = mo.maxent_loop(K, G * (1 + 1e-15), err, pr["omega"], mesh, reduce_singular_space=1e-10, svd=svd, analyzers=False)
+        o["noise_A"], _ = gc.oracle_floor(o, lambda f: mo.maxent_loop(K, G * f, err, pr["omega"], mesh, reduce_singular_space=1e-10,
+                                                                     svd=svd, analyzers=False))
         return o
 
     # (a) one scalar error bar per spectrum
@@ -669,9 +669,9 @@ def test_maxent_loop_with_data_kernel():
         res = ml.run()
         assert len(K.S) == 40 and np.all(res.converged)
         o = mo.maxent_loop(Kmat, G, 1e-3, np.asarray(om), np.asarray(mesh), variant=variant, reduce_singular_space=1e-9)
-        o2 = mo.maxent_loop(Kmat, G * (1 + 1e-15), 1e-3, np.asarray(om), np.asarray(mesh), variant=variant,
-                            reduce_singular_space=1e-9, analyzers=False)
-        tol = np.maximum(1e-8, 10 * gc.running_max(gc.rel_A(o2["A"], o["A"])))
+        noise, _ = gc.oracle_floor(o, lambda f: mo.maxent_loop(Kmat, G * f, 1e-3, np.asarray(om), np.asarray(mesh), variant=variant,
+                                                              reduce_singular_space=1e-9, analyzers=False))
+        tol = np.maximum(1e-8, 10 * noise)
         assert np.all(gc.rel_A(res.A, o["A"]) <= tol), (kind, gc.rel_A(res.A, o["A"]) / tol)
         np.testing.assert_allclose(res.chi2, o["chi2"], rtol=1e-7)
         for name in ('LineFitAnalyzer', 'Chi2CurvatureAnalyzer', 'EntropyAnalyzer'):

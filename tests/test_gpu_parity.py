@@ -122,14 +122,12 @@ def test_small_random_batch_vs_oracle(torch_cuda, variant):
     for b in range(G.shape[0]):
         o = mo.maxent_loop(pr["K"], G[b], err, pr["omega"], mesh, variant=variant, probability=True,
                            reduce_singular_space=1e-10)
-        o2 = mo.maxent_loop(pr["K"], G[b] * (1 + 1e-15), err, pr["omega"], mesh, variant=variant,
-                            reduce_singular_space=1e-10, analyzers=False)
+        noise, nchi = gc.oracle_floor(o, lambda f: mo.maxent_loop(pr["K"], G[b] * f, err, pr["omega"], mesh, variant=variant,
+                                                                 reduce_singular_space=1e-10, analyzers=False))
         assert prob.n_sv == o["n_sv"]
-        noise = gc.running_max(gc.rel_A(o2["A"], o["A"]))
         tol = np.maximum(1e-8, 10 * noise)
         dA = gc.rel_A(res.A[b].cpu().numpy(), o["A"])
         assert np.all(dA <= tol), (variant, b, dA / tol)
-        nchi = gc.running_max(np.abs(o2["chi2"] / o["chi2"] - 1))
         assert np.all(np.abs(res.chi2[b].cpu().numpy() / o["chi2"] - 1) <= np.maximum(1e-8, 10 * nchi))
         idx = res.alpha_index[b].cpu().numpy()
         for slot, name in enumerate(gc.AN_NAMES[:3]):
@@ -240,17 +238,30 @@ def test_truncated_svd_of_the_benchmark_kernels(torch_cuda, shape):
 
 
 def test_full_rank_matrix_ends_with_the_full_svd(torch_cuda):
-    """A matrix that is not numerically rank deficient: the truncated route doubles its rank guess and ends with the
-    complete one-sided Jacobi (a slowly decaying DataKernel must not lose triplets silently)."""
+    """A matrix that is not numerically rank deficient: the truncated route doubles its rank guess and ends with every
+    column (a slowly decaying DataKernel must not lose triplets silently) -- a well conditioned one, and one with
+    200 singular values over six decades above a cluster at 1e-14 (the wide-kernel test below), where a one-sided Jacobi
+    on the matrix itself is still far from converged after sixty sweeps."""
     torch = torch_cuda
     from maxent_b200 import engine
     rng = np.random.RandomState(4)
     Kref = rng.randn(300, 220)
     U, S, V, info = engine.device_svd(torch.tensor(Kref, device="cuda"))
-    assert info.startswith("jacobi") and S.numel() == 220
+    assert info.startswith("range finder + jacobi, all 220") and S.numel() == 220
     Sref = np.linalg.svd(Kref, compute_uv=False)
     np.testing.assert_allclose(S.cpu().numpy(), Sref, rtol=1e-13)
     assert float(((U * S) @ V.T - torch.tensor(Kref, device="cuda")).abs().max()) < 1e-12
+    Uo, _ = np.linalg.qr(rng.randn(284, 240))
+    Vo, _ = np.linalg.qr(rng.randn(240, 240))
+    So = np.concatenate([np.logspace(0, -6, 200), 1e-14 * np.ones(40)])
+    Kref = (Uo * So) @ Vo.T
+    U, S, V, info = engine.device_svd(torch.tensor(Kref, device="cuda"))
+    Sref = np.linalg.svd(Kref, compute_uv=False)
+    assert S.numel() == 240 and int((S >= 1e-9).sum()) == 200
+    assert np.max(np.abs(S.cpu().numpy() - Sref)) < 2e-13                  # absolute, |K| = S[0] = 1
+    assert float(((U * S) @ V.T - torch.tensor(Kref, device="cuda")).abs().max()) < 1e-13
+    UtU = (U[:, :200].T @ U[:, :200]).cpu().numpy()
+    assert np.max(np.abs(UtU - np.eye(200))) < 1e-6        # left vectors of S >= 1e-6: orthonormal to ~eps * S[0] / S[k]
 
 
 def test_project_data(torch_cuda):
@@ -401,9 +412,9 @@ def test_per_spectrum_default_models(torch_cuda):
             one = engine.run_sweep(pb, G[b], mesh * 120)
             o = mo.maxent_loop(pr["K"], G[b], pr["err"], pr["omega"], mesh, D=models[b], variant=variant,
                                reduce_singular_space=1e-10, analyzers=False)
-            o2 = mo.maxent_loop(pr["K"], G[b] * (1 + 1e-15), pr["err"], pr["omega"], mesh, D=models[b], variant=variant,
-                                reduce_singular_space=1e-10, analyzers=False)
-            tol = np.maximum(1e-8, 10 * gc.running_max(gc.rel_A(o2["A"], o["A"])))
+            noise, _ = gc.oracle_floor(o, lambda f: mo.maxent_loop(pr["K"], G[b] * f, pr["err"], pr["omega"], mesh, D=models[b],
+                                                                  variant=variant, reduce_singular_space=1e-10, analyzers=False))
+            tol = np.maximum(1e-8, 10 * noise)
             A = res.A[b].cpu().numpy()
             assert np.all(gc.rel_A(A, o["A"]) <= tol), (variant, b, gc.rel_A(A, o["A"]) / tol)
             assert np.all(gc.rel_A(A, one.A[0].cpu().numpy()) <= tol), (variant, b)
@@ -412,13 +423,15 @@ def test_per_spectrum_default_models(torch_cuda):
         engine.run_sweep(prob, G, mesh * 120, D=models[:2])
 
 
-@pytest.mark.parametrize("n_sv_target", [45, 62, 70, 78])
+@pytest.mark.parametrize("n_sv_target", [45, 62, 70, 78, 96, 128, 200])
 def test_all_kernel_instantiations_vs_oracle(torch_cuda, n_sv_target):
-    """Every tile count of the sweep kernel (NT = ceil(n_sv / 8): lean 8-warp solver up to 56, register-split
-    solver up to 64, one CTA per SM above) on a DataKernel whose singular values decay slowly, vs the oracle."""
+    """Every tile count of the sweep kernel (NT = ceil(n_sv / 8): all eight warps solve up to 56, four above; the wide
+    instantiations with Z, J and the factors in the workspace for 81 <= n_sv <= 256: NT = 12, 16, 32 here) on a
+    DataKernel whose singular values decay slowly, vs the oracle.  The reference keeps every singular value above the
+    cut, whatever their number (python/kernels.py:101-122)."""
     from maxent_b200 import engine
     rng = np.random.RandomState(100 + n_sv_target)
-    n_tau, n_om = 140, 96
+    n_tau, n_om = (140, 96) if n_sv_target <= 80 else (n_sv_target + 84, n_sv_target + 40)
     om = mo.linear_omega_mesh(-4, 4, n_om)
     tau = np.linspace(0, 1, n_tau)
     # smooth positive kernel + a random part so that exactly n_sv_target singular values pass the cut
@@ -436,9 +449,9 @@ def test_all_kernel_instantiations_vs_oracle(torch_cuda, n_sv_target):
     res = engine.run_sweep(prob, G, mesh * n_tau, probability=True)
     for b in range(2):
         o = mo.maxent_loop(K, G[b], 1e-4, om, mesh, probability=True, reduce_singular_space=1e-9, analyzers=False)
-        o2 = mo.maxent_loop(K, G[b] * (1 + 1e-15), 1e-4, om, mesh, reduce_singular_space=1e-9, analyzers=False)
+        noise, _ = gc.oracle_floor(o, lambda f: mo.maxent_loop(K, G[b] * f, 1e-4, om, mesh, reduce_singular_space=1e-9, analyzers=False))
         assert o["n_sv"] == n_sv_target
-        tol = np.maximum(1e-8, 10 * gc.running_max(gc.rel_A(o2["A"], o["A"])))
+        tol = np.maximum(1e-8, 10 * noise)
         dA = gc.rel_A(res.A[b].cpu().numpy(), o["A"])
         assert np.all(dA <= tol), (n_sv_target, b, dA / tol)
         np.testing.assert_allclose(res.chi2[b].cpu().numpy(), o["chi2"], rtol=1e-7)
@@ -486,8 +499,8 @@ def _full_size_vs_oracle(tmp_path, first, n, extra=()):
 
 def test_full_size_sample_vs_oracle(torch_cuda, tmp_path):
     """BASELINE config 3/5 shape (n_tau = 2000, n_omega = 1000, 60 alphas, cut 1e-11): the first four spectra of the
-    benchmark batch against the oracle run on the host cores (four oracle runs per spectrum: three rounding-level
-    perturbations -- G * (1 +- 1e-15), the other LAPACK SVD driver -- measure the oracle's own noise floor per alpha).  Identical LineFit / Chi2Curvature picks; A and chi2
+    benchmark batch against the oracle run on the host cores (six oracle runs per spectrum: five rounding-level
+    perturbations -- G * (1 +- 1e-15), G * (1 + 2e-15), the kernel entries moved by +-1e-15, the other LAPACK SVD driver -- measure the oracle's own noise floor per alpha).  Identical LineFit / Chi2Curvature picks; A and chi2
     within 1e-8 wherever the oracle reproduces itself, within 10x its measured floor in the small-alpha tail."""
     _full_size_vs_oracle(tmp_path, 0, 4)
 
