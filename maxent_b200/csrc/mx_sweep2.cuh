@@ -139,9 +139,12 @@ __host__ __device__ constexpr int tri(int I, int J) { return I * (I + 1) / 2 + J
 // ------------------------------------------------------------------------------------------
 // sizes of the "lean" blocked Cholesky (see below): how many tiles of the factor a warp parks in shared memory
 // ------------------------------------------------------------------------------------------
+#ifndef MX_LEAN_RTILES
+#define MX_LEAN_RTILES 10       // strictly-lower tiles of the factor a warp keeps in registers
+#endif
 __host__ __device__ constexpr int lean_nsm(int NT) {
     int nsm = 0;
-    while (nsm < NT && (NT - 1 - nsm) * (NT - nsm) / 2 > 10) ++nsm;
+    while (nsm < NT && (NT - 1 - nsm) * (NT - nsm) / 2 > MX_LEAN_RTILES) ++nsm;
     return nsm;
 }
 __host__ __device__ constexpr int lean_nsmt(int NT) {          // strictly-lower tiles of the factor a warp parks in shared memory
@@ -174,7 +177,9 @@ struct Lean {
 __host__ __device__ constexpr int solver_warps(int NT) { return NT <= 7 ? NWARP : NWARP / 2; }
 __host__ __device__ constexpr int stage_count(int NT) {
     int need = NT * NT;                                                          // in 8x8 tiles
+#ifndef MX_LEAN_SPILLOVER           // the parked tiles may run past the ring into a few KB of their own (STAGE_AREA)
     if (solver_warps(NT) * lean_nsmt(NT) > need) need = solver_warps(NT) * lean_nsmt(NT);
+#endif
     if (NWARP * NT > need) need = NWARP * NT;
     // partial Z tiles of the H-pass: Zfull + (NKG - 1) triangles, minus what J and the trial vectors behind the ring hold
     const int hneed = NT * NT + (NKG - 2) * (NT * (NT + 1) / 2) - 2 * NT;
@@ -203,7 +208,9 @@ struct Lay {
     static constexpr int NTRI = NT * (NT + 1) / 2;
     static constexpr int STAGE_D = CH * NT * 64;
     static constexpr int NST = WIDE ? 0 : stage_count(NT);
-    static constexpr int STAGE_AREA = WIDE ? NWARP * 8 * SP : NST * STAGE_D;   // wide: only the y partials of the T-pass
+    static constexpr int LEAN_AREA = WIDE ? 0 : solver_warps(NT) * Lean<NT>::NSMT * 64;
+    static constexpr int STAGE_AREA = WIDE ? NWARP * 8 * SP                     // wide: only the y partials of the T-pass
+                                           : (NST * STAGE_D > LEAN_AREA ? NST * STAGE_D : LEAN_AREA);
     static constexpr int o_stage = 0;                              // NST x STAGE_D ; aliases: Zfull [NT*NT*64], yred [NWARP][8][SP], parked Cholesky tiles
     static constexpr int o_J = o_stage + STAGE_AREA;            // NTRI tiles, C layout (also: partial Z tiles of the H-pass, parked tiles of the log-det)
     static constexpr int o_tb = o_J + (WIDE ? 0 : NTRI * 64);      // [8][SP] trial vectors t_b = v - dv_b  (the accepted one IS the new v, levenberg_minimizer.py:239)
@@ -225,7 +232,7 @@ struct Lay {
     static constexpr int total = o_bar + 2 * NST;
     static_assert(WIDE || NT * NT * 64 <= NST * STAGE_D, "Zfull must fit in the staging area");
     static_assert(NWARP * 8 * SP <= STAGE_AREA, "yred must fit in the staging area");
-    static_assert(WIDE || solver_warps(NT) * Lean<NT>::NSMT * 64 <= NST * STAGE_D, "the parked tiles of the solver warps must fit in the staging area");
+    static_assert(WIDE || solver_warps(NT) * Lean<NT>::NSMT * 64 <= STAGE_AREA, "the parked tiles of the solver warps must fit in the staging area");
     static_assert(WIDE || Lean<NT>::NSMT <= NTRI, "the parked tiles of the log-det factorisation must fit in the J area");
     static_assert(WIDE || NT * NT * 64 + (NKG - 1) * NTRI * 64 <= o_ctb, "partial Z tiles of the H-pass must fit behind Zfull");
 };
@@ -1364,7 +1371,7 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
         // every solver warp factorises one shifted Hessian at a time; the strictly-lower tiles of the leading block
         // columns are parked in this warp's slice of the idle staging ring
         constexpr int NSOLVE = WIDE ? NWARP : solver_warps(NT);
-        double* const Lsm = sm + LY::o_stage + LY::NST * LY::STAGE_D - (warp + 1) * LN::NSMT * 64;
+        double* const Lsm = sm + LY::o_stage + LY::STAGE_AREA - (warp + 1) * LN::NSMT * 64;
         for (int u = warp; u < nuniq && warp < NSOLVE; u += NSOLVE) {
             const double mu = ctl.umu[u];
             auto load = [&](int I, int J) -> double2 {

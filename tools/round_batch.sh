@@ -16,4 +16,5 @@ timeout 900 compute-sanitizer --tool memcheck python -c 'import __graft_entry__ 
 timeout 900 compute-sanitizer --tool memcheck python tools/sanitize_run.py > $O/r02_sanitizer_memcheck_fullshape.txt 2>&1; echo "memcheck full-shape rc=$?"; tail -2 $O/r02_sanitizer_memcheck_fullshape.txt
 python tools/config_latency.py > $O/r02_config_latency.json 2> $O/r02_config_latency.err; echo "latency rc=$?"
 python tools/phase_times.py > $O/r02_phase_times.txt 2>&1; echo "phases rc=$?"
+python tools/wide_bench.py > $O/r02_wide_bench.json 2> $O/r02_wide_bench.err; echo "wide rc=$?"
 ls -la $O/r02b_sweep2_full.ncu-rep

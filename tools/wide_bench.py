@@ -1,0 +1,41 @@
+#!/usr/bin/env python
+"""Throughput of the wide instantiations of the sweep kernel (80 < n_sv <= 256) on a synthetic DataKernel whose
+singular values decay slowly, next to the oracle's time for one spectrum on one host core.
+
+    python tools/wide_bench.py [n_sv ...]        # default 56 96 128 200
+"""
+import json, os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from maxent_b200 import engine
+from oracle import maxent_oracle as mo           # inputs and the CPU timing only
+
+out = []
+for n_sv in [int(x) for x in sys.argv[1:]] or [56, 96, 128, 200]:
+    rng = np.random.RandomState(100 + n_sv)
+    n_tau, n_om, B = 600, 400, 296
+    om = mo.linear_omega_mesh(-4, 4, n_om)
+    U, _ = np.linalg.qr(rng.randn(n_tau, n_om))
+    V, _ = np.linalg.qr(rng.randn(n_om, n_om))
+    S = np.concatenate([np.logspace(0, -6, n_sv), 1e-14 * np.ones(n_om - n_sv)])
+    K = (U * S) @ V.T
+    A_true = np.exp(-(om - 0.5) ** 2) + 0.5 * np.exp(-(om + 1.5) ** 2 / 0.5)
+    delta = mo.omega_delta(om)
+    G = (K * delta[None, :]) @ A_true + 1e-4 * rng.randn(B, n_tau)
+    mesh = mo.log_alpha_mesh(0.5, 500, 20)
+    prob = engine.SharedProblem(K, 1e-4, mo.flat_default_model(om), delta, reduce_singular_space=1e-9)
+    Gd = torch.as_tensor(G, device="cuda")
+    engine.run_sweep(prob, Gd[:8], mesh * n_tau)
+    torch.cuda.synchronize(); t0 = time.time()
+    res = engine.run_sweep(prob, Gd, mesh * n_tau)
+    torch.cuda.synchronize(); t1 = time.time()
+    t2 = time.time()
+    o = mo.maxent_loop(K, G[0], 1e-4, om, mesh, reduce_singular_space=1e-9, analyzers=False)
+    t3 = time.time()
+    row = dict(n_sv=prob.n_sv, spectra=B, n_omega=n_om, n_alpha=20, gpu_s=round(t1 - t0, 4),
+               spectra_per_s=round(B / (t1 - t0), 1), lm_iterations_per_spectrum=float(res.n_iter.sum()) / B,
+               oracle_one_spectrum_one_core_s=round(t3 - t2, 2), converged=bool((res.status & 1).all()),
+               chi2_rel_dev_vs_oracle=float(np.max(np.abs(res.chi2[0].cpu().numpy() / o["chi2"] - 1))))
+    print(json.dumps(row)); sys.stdout.flush()
+    out.append(row)
