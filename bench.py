@@ -35,7 +35,7 @@ UNIT = "spectra/s"
 # DMMA m8n8k4 and DFMA both saturate at 37.0 TFLOP/s).  MEASURED_PEAKS.json holds no FP64 figure.
 FP64_PEAK_FALLBACK_TFLOPS = 37.0
 # DRAM traffic of the sweep kernel from the ncu capture under profiles/ (bytes read + written, per spectrum)
-NCU_DRAM_BYTES_PER_SPECTRUM = int((3.449856e6 + 524.792832e6) / 296)   # profiles/r02a_sweep2_ncu_full_summary.json
+NCU_DRAM_BYTES_PER_SPECTRUM = int((6.706432e6 + 3.062703e9) / 296)   # profiles/r02c_sweep2_ncu_full_summary.json
 
 
 def parse_args():
@@ -381,11 +381,14 @@ def run_native(a):
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": NCU_DRAM_BYTES_PER_SPECTRUM * B, "traffic_unit": "bytes per launch",
                          "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one 296-spectrum "
-                                           "launch (profiles/r02a_*), scaled to this launch's spectra; algorithmic bytes per spectrum = "
+                                           "launch (profiles/r02c_*), scaled to this launch's spectra; algorithmic bytes per spectrum = "
                                            "G in + A(alpha) out = %d" % (a.n_tau * 8 + a.n_alpha * a.n_omega * 8),
-                         "traffic_note": "accepted: %.1fx the algorithmic bytes -- the per-CTA scratch rows of w = dH/dx are written "
-                                         "through to HBM; the whole DRAM traffic of the kernel is ~0.1 %% of the HBM bandwidth "
-                                         "(FP64-pipe bound)" % (NCU_DRAM_BYTES_PER_SPECTRUM / (a.n_tau * 8 + a.n_alpha * a.n_omega * 8)),
+                         "traffic_note": "accepted: %.0fx the algorithmic bytes = ~23 GB/s, 0.3 %% of the HBM bandwidth (the kernel is "
+                                         "FP64-pipe bound).  It is write-back of L2 lines, not re-reads: the solver's register spills "
+                                         "(128-register cap for two CTAs per SM; 58 GB of local-memory stores per 296-spectrum wave "
+                                         "into L2) and the per-CTA scratch rows of w = dH/dx share the L2 with the streamed A(alpha) "
+                                         "output, and ~5 %% of those lines are evicted dirty"
+                                         % (NCU_DRAM_BYTES_PER_SPECTRUM / (a.n_tau * 8 + a.n_alpha * a.n_omega * 8)),
                          "peak_measured_in_run": peak_meas,
                          "kernel": "mx2::sweep2_kernel", "kernel_ms": kernel_ms,
                          "kernel_share_of_step": kernel_ms / (dev_ms / a.steps),

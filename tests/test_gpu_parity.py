@@ -460,6 +460,40 @@ def test_all_kernel_instantiations_vs_oracle(torch_cuda, n_sv_target):
     assert bool((res.status & 1).all())
 
 
+@pytest.mark.parametrize("variant,marquardt", [("plusminus", False), ("bryan", False), ("normal", True)])
+def test_wide_instantiations_other_variants(torch_cuda, variant, marquardt):
+    """The wide instantiations (n_sv = 100 -> 16 tiles) for the plus-minus and Bryan cost functions and for Marquardt's
+    damping, vs the oracle (same contract as above)."""
+    from maxent_b200 import engine
+    n_sv, n_tau, n_om = 100, 184, 140
+    rng = np.random.RandomState(7)
+    om = mo.linear_omega_mesh(-4, 4, n_om)
+    U, _ = np.linalg.qr(rng.randn(n_tau, n_om))
+    V, _ = np.linalg.qr(rng.randn(n_om, n_om))
+    S = np.concatenate([np.logspace(0, -6, n_sv), 1e-14 * np.ones(n_om - n_sv)])
+    K = (U * S) @ V.T
+    A_true = np.exp(-(om - 0.5) ** 2) + 0.5 * np.exp(-(om + 1.5) ** 2 / 0.5)
+    if variant == "plusminus":
+        A_true = A_true - 0.8 * np.exp(-(om - 2.0) ** 2 / 0.3)
+    delta = mo.omega_delta(om)
+    G = (K * delta[None, :]) @ A_true + 1e-4 * rng.randn(2, n_tau)
+    D = mo.flat_default_model(om)
+    mesh = mo.log_alpha_mesh(0.5, 500, 6)
+    prob = engine.SharedProblem(K, 1e-4, D, delta, variant=variant, reduce_singular_space=1e-9)
+    assert prob.n_sv == n_sv
+    lm = engine.LMParams(marquardt=marquardt)
+    res = engine.run_sweep(prob, G, mesh * n_tau, lm=lm)
+    for b in range(2):
+        kw = dict(variant=variant, reduce_singular_space=1e-9, analyzers=False, lm_options=dict(marquardt=marquardt))
+        o = mo.maxent_loop(K, G[b], 1e-4, om, mesh, **kw)
+        noise, nchi = gc.oracle_floor(o, lambda f: mo.maxent_loop(K, G[b] * f, 1e-4, om, mesh, **kw))
+        tol = np.maximum(1e-8, 10 * noise)
+        dA = gc.rel_A(res.A[b].cpu().numpy(), o["A"])
+        assert np.all(dA <= tol), (variant, b, dA / tol)
+        assert np.all(np.abs(res.chi2[b].cpu().numpy() / o["chi2"] - 1) <= np.maximum(1e-8, 10 * nchi))
+    assert bool((res.status & 1).all())
+
+
 def _full_size_vs_oracle(tmp_path, first, n, extra=()):
     import os, subprocess, sys
     from maxent_b200 import engine, batched

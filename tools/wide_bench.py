@@ -26,10 +26,14 @@ for n_sv in [int(x) for x in sys.argv[1:]] or [56, 96, 128, 200]:
     mesh = mo.log_alpha_mesh(0.5, 500, 20)
     prob = engine.SharedProblem(K, 1e-4, mo.flat_default_model(om), delta, reduce_singular_space=1e-9)
     Gd = torch.as_tensor(G, device="cuda")
-    engine.run_sweep(prob, Gd[:8], mesh * n_tau)
-    torch.cuda.synchronize(); t0 = time.time()
-    res = engine.run_sweep(prob, Gd, mesh * n_tau)
-    torch.cuda.synchronize(); t1 = time.time()
+    engine.run_sweep(prob, Gd, mesh * n_tau)             # warm-up at the full batch size (allocator, module loading)
+    best = 1e30
+    for _ in range(3):
+        torch.cuda.synchronize(); t0 = time.time()
+        res = engine.run_sweep(prob, Gd, mesh * n_tau)
+        torch.cuda.synchronize(); t1 = time.time()
+        best = min(best, t1 - t0)
+    t0, t1 = 0.0, best
     t2 = time.time()
     o = mo.maxent_loop(K, G[0], 1e-4, om, mesh, reduce_singular_space=1e-9, analyzers=False)
     t3 = time.time()
