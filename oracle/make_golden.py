@@ -159,6 +159,7 @@ def main():
     mesh_case(m)
     covariance_case(m)
     iomega_case(m)
+    low_temperature_case(m)
     config4_case(m)
 
 
@@ -347,6 +348,18 @@ def config4_case(m):
     print("g13", out["ref_n_sv"], out["ref_wall"], {k: v for k, v in out.items() if k.startswith("ref_idx_")})
 
 
+def low_temperature_case(m):
+    """G15: a kernel that keeps more than 80 singular values -- beta = 1000, n_tau = 1000, n_omega = 500, the reference's
+    default cut 1e-14 (83 values with LAPACK; 81 above the numerical rank floor) -- through TauMaxEnt, 30 alphas."""
+    tau, G, om = synthetic(1000, 500, beta=1000.0)
+    amesh = m.LogAlphaMesh(0.01, 2000, 30)
+    out, tm, res = run_reference(m, tau, G, 1.e-4, om, amesh, reduce_singular_space=1e-14)
+    for k in ("ref_H", "ref_v"):
+        out.pop(k)
+    np.savez_compressed(os.path.join(GOLD, "g15_low_temperature_wide.npz"), **out)
+    print("g15", out["ref_n_sv"], out["ref_wall"], {k: v for k, v in out.items() if k.startswith("ref_idx_")})
+
+
 def iomega_case(m):
     """G14: continuation of Matsubara data G(i omega_n) with a REAL spectral function.  The reference's IOmegaKernel
     (python/kernels.py:283-346) supplies the complex kernel; chi2 = sum |G - K H|^2 / sigma^2 (ComplexChi2.f,
@@ -396,7 +409,9 @@ def iomega_case(m):
 
 
 if __name__ == "__main__":
-    if "--iomega-only" in sys.argv:
+    if "--low-temperature-only" in sys.argv:
+        low_temperature_case(import_reference())
+    elif "--iomega-only" in sys.argv:
         iomega_case(import_reference())
     elif "--elementwise-only" in sys.argv:
         elementwise_cases(import_reference())

@@ -31,11 +31,15 @@ def torch_cuda():
 # ----------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["g1_semicircular_prob.npz", "g2_synth_200x100.npz", "g3_plusminus_offdiag.npz",
                                   "g4_bryan_200x100.npz", "g5_config1_cut1e-11.npz",
-                                  "g5b_config1_default_cut.npz"])
+                                  "g5b_config1_default_cut.npz", "g15_low_temperature_wide.npz"])
 def test_golden_reference_parity(torch_cuda, name):
     g = gc.load_golden(name)
     prob, res = gc.run_fixture(g)
-    if name.startswith("g5b"):
+    if name.startswith("g15"):
+        # beta = 1000 at the default cut: 82 singular values in the reference, 81 above the numerical rank floor here --
+        # more than the shared-memory instantiations hold: the wide instantiation (12 tiles) against the real reference
+        assert 80 < prob.n_sv <= int(g["ref_n_sv"]) and prob.config["smem_bytes"] > 0
+    elif name.startswith("g5b"):
         # absolute cut 1e-14 (the reference default) sits inside the rounding noise of the singular values:
         # how many of them pass depends on the SVD implementation (LAPACK gesdd: 76, device Jacobi: ~66), so
         # the engine honours the cut only down to the numerical rank (engine.SharedProblem rank_floor);

@@ -105,6 +105,17 @@ def test_config1_bit_identical(golden_dir, name):
     assert out["analyzers"]["EntropyAnalyzer"]["alpha_index"] == 42
 
 
+def test_low_temperature_kernel_bit_identical(golden_dir):
+    """beta = 1000: the reference keeps 82 singular values at its default cut -- the oracle for the wide
+    instantiations of the sweep kernel (n_sv > 80)."""
+    g = _load(golden_dir, "g15_low_temperature_wide.npz")
+    out = _run(g)
+    assert out["n_sv"] == int(g["ref_n_sv"]) == 82
+    _check_identical(out, g)
+    assert out["analyzers"]["LineFitAnalyzer"]["alpha_index"] == int(g["ref_idx_LineFitAnalyzer"]) == 14
+    assert out["analyzers"]["Chi2CurvatureAnalyzer"]["alpha_index"] == int(g["ref_idx_Chi2CurvatureAnalyzer"]) == 17
+
+
 def test_meshes_and_kernel():
     """test/python/tau_kernel.py:27-69 : independent kernel formula to 1e-15; U S V^T reconstructs K."""
     tau = np.linspace(0, 10, 50)
