@@ -9,7 +9,7 @@
 // mu, 1.3 mu, 1.3^2 mu ... that is decided by comparisons of the Q values.  Instead of evaluating the
 // chain one trial at a time (latency bound), the CTA *speculates*: it plans the next up-to-8 damping
 // values the reference would visit, factorises the 8 shifted Hessians (one warp per matrix, DMMA-blocked "lean"
-// Cholesky) and evaluates the 8 trial vectors in ONE pass over
+// L D L^T) and evaluates the 8 trial vectors in ONE pass over
 // V' where the 8 trials are the M dimension of the FP64 tensor-core MMA (m8n8k4):
 //     T-pass:  x = V' t_b ; H = D exp(x) ; y_b = V'^T H ; S_b ; w_b -> scratch      (8 trials)
 //     H-pass:  Z = V'^T diag(w) V'                                                   (accepted point)
@@ -28,6 +28,10 @@
 // V' streams L2 -> shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier) in the
 // swizzled 8x8-tile layout written by mx_layout_V.  A bulk copy costs the CTA ~360 cycles whatever its size
 // (tools/tma_stream_bench.cu), so a chunk is one copy of NWARP k-tiles: one tile per warp and step in the T-pass.
+//
+// Instantiations: NT = 4..10 tiles of 8 singular-space columns (n_sv <= 80) keep every matrix in shared memory and
+// registers as described; NT = 12, 16, 24, 32 (n_sv <= 256, "wide") run the same code with Z, J and the factors in a
+// per-CTA slice of the global workspace and V' read from L2 directly (see is_wide below).
 #pragma once
 #include <stdlib.h>
 #include "mx_common.cuh"
