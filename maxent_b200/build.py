@@ -16,7 +16,7 @@ LIB = os.path.join(HERE, "libmaxent_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
-SWEEP2_NT = (4, 5, 6, 7, 8, 9, 10, 12, 16, 24, 32)    # spectrum-per-CTA engine (csrc/mx_sweep2.cuh); > 10: wide
+SWEEP2_NT = (4, 5, 6, 7, 8, 9, 10, 12, 16, 20, 24, 28, 32)    # spectrum-per-CTA engine (csrc/mx_sweep2.cuh); > 10: wide
 
 
 def _units():

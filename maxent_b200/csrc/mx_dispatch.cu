@@ -10,7 +10,9 @@ int sweep2_nt9(const mx::SweepArgs&, cudaStream_t, bool, int*, int*);
 int sweep2_nt10(const mx::SweepArgs&, cudaStream_t, bool, int*, int*);
 int sweep2_nt12(const mx::SweepArgs&, cudaStream_t, bool, int*, int*);
 int sweep2_nt16(const mx::SweepArgs&, cudaStream_t, bool, int*, int*);
+int sweep2_nt20(const mx::SweepArgs&, cudaStream_t, bool, int*, int*);
 int sweep2_nt24(const mx::SweepArgs&, cudaStream_t, bool, int*, int*);
+int sweep2_nt28(const mx::SweepArgs&, cudaStream_t, bool, int*, int*);
 int sweep2_nt32(const mx::SweepArgs&, cudaStream_t, bool, int*, int*);
 long long sweep2_wide_doubles(int nt);
 int sweep2_threads();
@@ -51,7 +53,9 @@ int dispatch_sweep(SweepArgs& a, cudaStream_t stream, bool query, int engine, in
         case 10: return mx2::sweep2_nt10(a, stream, query, o_smem, o_grid);
         case 12: return mx2::sweep2_nt12(a, stream, query, o_smem, o_grid);
         case 16: return mx2::sweep2_nt16(a, stream, query, o_smem, o_grid);
+        case 20: return mx2::sweep2_nt20(a, stream, query, o_smem, o_grid);
         case 24: return mx2::sweep2_nt24(a, stream, query, o_smem, o_grid);
+        case 28: return mx2::sweep2_nt28(a, stream, query, o_smem, o_grid);
         default: return mx2::sweep2_nt32(a, stream, query, o_smem, o_grid);
     }
 }

@@ -771,12 +771,12 @@ __device__ __forceinline__ void wide_solve(const double* Lw, const double* dinv,
     }
 }
 
-// Wide H-pass: Z = V'^T diag(w) V' in blocks of 8 x 4 tiles per warp (accumulators in registers), every block a full
+// Wide H-pass: Z = V'^T diag(w) V' in blocks of 4 x 4 tiles per warp (accumulators in registers), every block a full
 // pass over V' in k order -- one warp per tile, hence one fixed summation order and no reduction between warps.
 template <int NT>
 __device__ __forceinline__ void hpass_wide(const double* __restrict__ Vt, const double* __restrict__ wrow, int n_kt, double* Zf,
                                            int warp, int lane, int r, int q, int offY0, int offY1) {
-    constexpr int BI = 8, BJ = 4;
+    constexpr int BI = 4, BJ = 4;
     constexpr int NBI = (NT + BI - 1) / BI, NBJ = (NT + BJ - 1) / BJ;
     int cnt = 0;
     for (int bi = 0; bi < NBI; ++bi)
@@ -788,23 +788,43 @@ __device__ __forceinline__ void hpass_wide(const double* __restrict__ Vt, const 
             for (int i = 0; i < BI; ++i)
 #pragma unroll
                 for (int j = 0; j < BJ; ++j) { z[i][j][0] = 0.0; z[i][j][1] = 0.0; }
-            for (int kt = 0; kt < n_kt; ++kt) {
-                const double2 w = *reinterpret_cast<const double2*>(wrow + kt * 8 + 2 * q);
+            // fragments of the block's rows (I0..) and columns (J0..) of one k-tile, both omega halves; the next k-tile is
+            // fetched from L2 while the MMAs of the current one issue
+            auto fetch = [&](int kt, double2& w, double (&fi)[2][BI], double (&fj)[2][BJ]) {
+                if (kt >= n_kt) return;
+                w = *reinterpret_cast<const double2*>(wrow + kt * 8 + 2 * q);
                 const double* tile = Vt + (size_t)kt * NT * 64;
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int off = e ? offY1 : offY0;
+#pragma unroll
+                    for (int i = 0; i < BI; ++i) fi[e][i] = (I0 + i < NT) ? tile[(I0 + i) * 64 + off] : 0.0;
+#pragma unroll
+                    for (int j = 0; j < BJ; ++j) fj[e][j] = (J0 + j < NT) ? tile[(J0 + j) * 64 + off] : 0.0;
+                }
+            };
+            double2 wn = make_double2(0.0, 0.0);
+            double fin[2][BI], fjn[2][BJ];
+            fetch(0, wn, fin, fjn);
+            for (int kt = 0; kt < n_kt; ++kt) {
+                const double2 w = wn;
+                double fi[2][BI], fj[2][BJ];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+#pragma unroll
+                    for (int i = 0; i < BI; ++i) fi[e][i] = fin[e][i];
+#pragma unroll
+                    for (int j = 0; j < BJ; ++j) fj[e][j] = fjn[e][j];
+                }
+                fetch(kt + 1, wn, fin, fjn);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
                     const double we = e ? w.y : w.x;
-                    double fi[BI], fj[BJ];
-#pragma unroll
-                    for (int i = 0; i < BI; ++i) fi[i] = (I0 + i < NT) ? we * tile[(I0 + i) * 64 + off] : 0.0;
-#pragma unroll
-                    for (int j = 0; j < BJ; ++j) fj[j] = (J0 + j < NT) ? tile[(J0 + j) * 64 + off] : 0.0;
 #pragma unroll
                     for (int i = 0; i < BI; ++i)
 #pragma unroll
                         for (int j = 0; j < BJ; ++j)
-                            if (J0 + j <= I0 + i && I0 + i < NT) dmma(z[i][j], fi[i], fj[j]);
+                            if (J0 + j <= I0 + i && I0 + i < NT) dmma(z[i][j], we * fi[e][i], fj[e][j]);
                 }
             }
 #pragma unroll
@@ -1313,38 +1333,60 @@ __global__ void __launch_bounds__(NTHR, ctas_per_sm<NT>()) sweep2_kernel(const S
     auto form_J = [&]() {
         const double* Zf = Zfull();
         const double alpha = ctl.alpha;
-        for (int t = warp; t < NTRI; t += NWARP) {
-            int I = 0;
-            while (tri(I + 1, 0) <= t) ++I;
-            const int J = t - tri(I, 0);
-            double c[2] = {0.0, 0.0};
-            const double2 zij = *reinterpret_cast<const double2*>(Zf + (I * NT + J) * 64 + 2 * lane);
+        // every warp owns the tiles t = warp, warp + NWARP, ...; G of them are formed at a time so that their accumulation
+        // chains (NT dependent MMA pairs each) interleave
+        constexpr int TPW = (NTRI + NWARP - 1) / NWARP;
+        constexpr int G = WIDE ? 2 : (TPW < 4 ? TPW : 4);
+        for (int t0 = warp; t0 < NTRI; t0 += NWARP * G) {
+            int tI[G], tJ[G];
+            double c[G][2];
+            double2 zij[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const int t = t0 + g * NWARP < NTRI ? t0 + g * NWARP : t0;     // a missing tile repeats the first one (not stored)
+                int I = 0;
+                while (tri(I + 1, 0) <= t) ++I;
+                tI[g] = I; tJ[g] = t - tri(I, 0);
+                c[g][0] = 0.0; c[g][1] = 0.0;
+                zij[g] = *reinterpret_cast<const double2*>(Zf + (tI[g] * NT + tJ[g]) * 64 + 2 * lane);
+            }
             if (!bryan) {
 #pragma unroll
                 for (int K = 0; K < NT; ++K) {
-                    const double2 zi = *reinterpret_cast<const double2*>(Zf + (I * NT + K) * 64 + 2 * lane);
-                    const double2 zj = *reinterpret_cast<const double2*>(Zf + (J * NT + K) * 64 + 2 * lane);
                     const double2 lm = *reinterpret_cast<const double2*>(sm + LY::o_lam + 8 * K + 2 * q);
-                    mma_nt(c, zi.x * lm.x, zi.y * lm.y, zj.x, zj.y);
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const double2 zi = *reinterpret_cast<const double2*>(Zf + (tI[g] * NT + K) * 64 + 2 * lane);
+                        const double2 zj = *reinterpret_cast<const double2*>(Zf + (tJ[g] * NT + K) * 64 + 2 * lane);
+                        mma_nt(c[g], zi.x * lm.x, zi.y * lm.y, zj.x, zj.y);
+                    }
                 }
-                c[0] = fma(a.eta, c[0], alpha * zij.x);       // maxent_cost_function.py:161-162 in singular space
-                c[1] = fma(a.eta, c[1], alpha * zij.y);
-            } else {                                           // M = eta Xi Z Xi
-                const double xr_ = a.eta * sm[LY::o_xi + 8 * I + r];
-                const double2 xc = *reinterpret_cast<const double2*>(sm + LY::o_xi + 8 * J + 2 * q);
-                c[0] = xr_ * zij.x * xc.x; c[1] = xr_ * zij.y * xc.y;
             }
-            if (I == J) {                                      // padded rows/columns: identity
-                const int i0 = 8 * I + r;
-                if (i0 >= s) { c[0] = (r == 2 * q) ? 1.0 : 0.0; c[1] = (r == 2 * q + 1) ? 1.0 : 0.0; }
-                else { if (8 * J + 2 * q >= s) c[0] = 0.0; if (8 * J + 2 * q + 1 >= s) c[1] = 0.0; }
-                if (r == 2 * q) sm[LY::o_jd + i0] = c[0];
-                if (r == 2 * q + 1) sm[LY::o_jd + i0] = c[1];
-            } else {
-                if (8 * I + r >= s || 8 * J + 2 * q >= s) c[0] = 0.0;
-                if (8 * I + r >= s || 8 * J + 2 * q + 1 >= s) c[1] = 0.0;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const int t = t0 + g * NWARP;
+                if (t >= NTRI) continue;
+                const int I = tI[g], J = tJ[g];
+                if (!bryan) {
+                    c[g][0] = fma(a.eta, c[g][0], alpha * zij[g].x);       // maxent_cost_function.py:161-162 in singular space
+                    c[g][1] = fma(a.eta, c[g][1], alpha * zij[g].y);
+                } else {                                           // M = eta Xi Z Xi
+                    const double xr_ = a.eta * sm[LY::o_xi + 8 * I + r];
+                    const double2 xc = *reinterpret_cast<const double2*>(sm + LY::o_xi + 8 * J + 2 * q);
+                    c[g][0] = xr_ * zij[g].x * xc.x; c[g][1] = xr_ * zij[g].y * xc.y;
+                }
+                if (I == J) {                                      // padded rows/columns: identity
+                    const int i0 = 8 * I + r;
+                    if (i0 >= s) { c[g][0] = (r == 2 * q) ? 1.0 : 0.0; c[g][1] = (r == 2 * q + 1) ? 1.0 : 0.0; }
+                    else { if (8 * J + 2 * q >= s) c[g][0] = 0.0; if (8 * J + 2 * q + 1 >= s) c[g][1] = 0.0; }
+                    if (r == 2 * q) sm[LY::o_jd + i0] = c[g][0];
+                    if (r == 2 * q + 1) sm[LY::o_jd + i0] = c[g][1];
+                } else {
+                    if (8 * I + r >= s || 8 * J + 2 * q >= s) c[g][0] = 0.0;
+                    if (8 * I + r >= s || 8 * J + 2 * q + 1 >= s) c[g][1] = 0.0;
+                }
+                *reinterpret_cast<double2*>(Jtiles() + (size_t)t * 64 + 2 * lane) = make_double2(c[g][0], c[g][1]);
             }
-            *reinterpret_cast<double2*>(Jtiles() + (size_t)t * 64 + 2 * lane) = make_double2(c[0], c[1]);
         }
         __syncthreads();
         if (warp == 0) {

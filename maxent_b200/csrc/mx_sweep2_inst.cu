@@ -8,6 +8,6 @@ int MX_CAT(sweep2_nt, MX_NT)(const mx::SweepArgs& a, cudaStream_t stream, bool q
 }
 #if MX_NT == 7
 int sweep2_threads() { return threads_per_cta(); }
-long long sweep2_wide_doubles(int nt) { return nt == 12 ? wide_doubles(12) : nt == 16 ? wide_doubles(16) : nt == 24 ? wide_doubles(24) : nt == 32 ? wide_doubles(32) : 0; }
+long long sweep2_wide_doubles(int nt) { return wide_doubles(nt); }
 #endif
 }  // namespace mx2

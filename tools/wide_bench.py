@@ -34,12 +34,15 @@ for n_sv in [int(x) for x in sys.argv[1:]] or [56, 96, 128, 200]:
         torch.cuda.synchronize(); t1 = time.time()
         best = min(best, t1 - t0)
     t0, t1 = 0.0, best
+    rp = engine.run_sweep(prob, Gd[:148], mesh * n_tau, phase_timers=True)     # one CTA per SM: uncontended phase times
+    cyc = rp.phase_cycles.double().cpu().numpy().sum(0) / 1965.0 / float(rp.n_iter.sum())
+    phases = dict(zip(["planner", "solver", "T-pass", "H-pass", "gradient", "J assembly", "other", "replay"], np.round(cyc, 1).tolist()))
     t2 = time.time()
     o = mo.maxent_loop(K, G[0], 1e-4, om, mesh, reduce_singular_space=1e-9, analyzers=False)
     t3 = time.time()
     row = dict(n_sv=prob.n_sv, spectra=B, n_omega=n_om, n_alpha=20, gpu_s=round(t1 - t0, 4),
                spectra_per_s=round(B / (t1 - t0), 1), lm_iterations_per_spectrum=float(res.n_iter.sum()) / B,
-               oracle_one_spectrum_one_core_s=round(t3 - t2, 2), converged=bool((res.status & 1).all()),
+               us_per_lm_iteration=phases, oracle_one_spectrum_one_core_s=round(t3 - t2, 2), converged=bool((res.status & 1).all()),
                chi2_rel_dev_vs_oracle=float(np.max(np.abs(res.chi2[0].cpu().numpy() / o["chi2"] - 1))))
     print(json.dumps(row)); sys.stdout.flush()
     out.append(row)
