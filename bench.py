@@ -35,7 +35,7 @@ UNIT = "spectra/s"
 # DMMA m8n8k4 and DFMA both saturate at 37.0 TFLOP/s).  MEASURED_PEAKS.json holds no FP64 figure.
 FP64_PEAK_FALLBACK_TFLOPS = 37.0
 # DRAM traffic of the sweep kernel from the ncu capture under profiles/ (bytes read + written, per spectrum)
-NCU_DRAM_BYTES_PER_SPECTRUM = int((6.706432e6 + 3.062703e9) / 296)   # profiles/r02c_sweep2_ncu_full_summary.json
+NCU_DRAM_BYTES_PER_SPECTRUM = int((6.98624e6 + 3.076533e9) / 296)   # profiles/r02c_sweep2_ncu_full_summary.json
 
 
 def parse_args():
