@@ -427,10 +427,10 @@ def test_per_spectrum_default_models(torch_cuda):
         engine.run_sweep(prob, G, mesh * 120, D=models[:2])
 
 
-@pytest.mark.parametrize("n_sv_target", [45, 62, 70, 78, 96, 128, 200])
+@pytest.mark.parametrize("n_sv_target", [45, 62, 70, 78, 96, 128, 150, 180, 200, 250])
 def test_all_kernel_instantiations_vs_oracle(torch_cuda, n_sv_target):
     """Every tile count of the sweep kernel (NT = ceil(n_sv / 8): all eight warps solve up to 56, four above; the wide
-    instantiations with Z, J and the factors in the workspace for 81 <= n_sv <= 256: NT = 12, 16, 32 here) on a
+    instantiations with Z, J and the factors in the workspace for 81 <= n_sv <= 256: NT = 12, 16, 20, 24, 28, 32 here) on a
     DataKernel whose singular values decay slowly, vs the oracle.  The reference keeps every singular value above the
     cut, whatever their number (python/kernels.py:101-122)."""
     from maxent_b200 import engine
